@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's controller interface, batched over B scenarios.
+
+Same names, call order and argument meaning as the reference
+(ctor -> SetWeights -> SetOutputReference -> Initialize -> GetNextInput*):
+  ControllerInterface::GetNextInput          include/controller_interface.h:46
+  NerveCenter::{SetWeights,SetOutputReference,Initialize,GetNextInput}
+                                             include/nerve_center.h:89-182
+  InputConstraints                           include/input_constraints.h:11-27
+Every method forwards to the C ABI (include/cmpc.h); all numerics run on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import check, f64, lib, ptr
+
+
+@dataclasses.dataclass
+class InputConstraints:
+    lower_bound: np.ndarray
+    upper_bound: np.ndarray
+    lower_rate_bound: np.ndarray
+    upper_rate_bound: np.ndarray
+    use_rate_constraints: bool = False  # never read by the reference either (mpc_qp_solver.cc:57-64)
+
+
+class NerveCenter:
+    """Batched NerveCenter: one cooperative / non-cooperative / centralised MPC per scenario."""
+
+    def __init__(self, plant: int, mode: int, batch: int = 1, p: int = 100, n_solver_iterations: Optional[int] = None,
+                 device: int = 0, constraints: Optional[InputConstraints] = None):
+        cfg = capi.default_config(plant, mode, batch)
+        cfg.p = p
+        if n_solver_iterations is not None:
+            cfg.n_iterations = n_solver_iterations
+        self.cfg = cfg
+        self.plant, self.mode, self.batch, self.p = plant, mode, batch, p
+        self.n_controllers = cfg.n_controllers
+        self.n_sub_control_inputs = cfg.n_sub_control_inputs
+        self.n_controlled_outputs = [cfg.n_controlled_outputs[c] for c in range(cfg.n_controllers)]
+        self.controlled_output_indices = [list(cfg.controlled_output_indices[c])[: self.n_controlled_outputs[c]]
+                                          for c in range(cfg.n_controllers)]
+        self.control_input_indices = [list(cfg.control_input_indices[c]) for c in range(cfg.n_controllers)]
+        self.nv = 2 * self.n_sub_control_inputs
+        self.nvo = 2 * (4 - self.n_sub_control_inputs)
+        n, nin = C.c_int(), C.c_int()
+        check(lib().cmpc_plant_dims(plant, C.byref(n), C.byref(nin)))
+        self.n_states, self.n_inputs = n.value, nin.value
+        self._h = C.c_void_p()
+        check(lib().cmpc_create(C.byref(cfg), device, C.byref(self._h)))
+        if constraints is not None:
+            for c in range(self.n_controllers):
+                self.SetConstraints(c, constraints)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().cmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup (nerve_center.h:98-122) -------------------------------------------------
+    def SetWeights(self, uwt: np.ndarray, ywts: Sequence[np.ndarray]):
+        """uwt: full 4x4 input weight; ywts: one n_y x n_y matrix per sub-controller
+        (tuple overload, nerve_center.h:113-116; sub-matrix selection :225-234)."""
+        uwt = f64(uwt)
+        for c in range(self.n_controllers):
+            idx = self.control_input_indices[c][: self.n_sub_control_inputs]
+            sub = f64(uwt[np.ix_(idx, idx)])
+            check(lib().cmpc_set_weights(self._h, c, ptr(sub), ptr(f64(ywts[c]))))
+
+    def SetOutputReference(self, y_ref: np.ndarray):
+        """y_ref: (p, 4) reference for all plant outputs over the horizon (or (4,), replicated)."""
+        y_ref = f64(y_ref)
+        if y_ref.ndim == 1:
+            y_ref = f64(np.tile(y_ref, (self.p, 1)))
+        assert y_ref.shape == (self.p, 4)
+        check(lib().cmpc_set_output_reference(self._h, ptr(y_ref)))
+
+    def SetConstraints(self, ctrl: int, ic: InputConstraints):
+        check(lib().cmpc_set_constraints(self._h, ctrl, ptr(f64(ic.lower_bound)), ptr(f64(ic.upper_bound)),
+                                         ptr(f64(ic.lower_rate_bound)), ptr(f64(ic.upper_rate_bound))))
+
+    def SetObserverGain(self, ctrl: int, M: np.ndarray):
+        M = f64(M)
+        assert M.shape == (self.n_states + 4, 4)
+        check(lib().cmpc_set_observer_gain(self._h, ctrl, ptr(M)))
+
+    def Initialize(self, x_init, u_init, u_init_full, y_init):
+        B = self.batch
+        bc = lambda a, k: f64(np.broadcast_to(f64(a), (B, k)))
+        check(lib().cmpc_initialize(self._h, ptr(bc(x_init, self.n_states)), ptr(bc(u_init, 4)),
+                                    ptr(bc(u_init_full, self.n_inputs)), ptr(bc(y_init, 4))))
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def GetNextInput(self, y) -> np.ndarray:
+        """y: (B, 4) host array -> u: (B, 4) (relative to the input offset), as the reference returns."""
+        y = f64(np.broadcast_to(f64(y), (self.batch, 4)))
+        u = np.empty((self.batch, 4))
+        check(lib().cmpc_get_next_input(self._h, ptr(y), ptr(u)))
+        return u
+
+    def GetNextInputDevice(self, y_dev_ptr: int, u_dev_ptr: int, stream: int = 0):
+        check(lib().cmpc_get_next_input_device(self._h, C.c_void_p(y_dev_ptr), C.c_void_p(u_dev_ptr),
+                                               C.c_void_p(stream)))
+
+    def step_info(self):
+        n = self.batch * self.n_controllers
+        st = np.zeros(n, dtype=np.int32); act = np.zeros(n, dtype=np.uint32); obj = np.zeros(n)
+        check(lib().cmpc_get_step_info(self._h, ptr(st), ptr(act), ptr(obj)))
+        shp = (self.batch, self.n_controllers)
+        return dict(status=st.reshape(shp), active=act.reshape(shp), objective=obj.reshape(shp))
+
+    # ---- closed loop --------------------------------------------------------------------
+    def run_closed_loop(self, x0, block_end, block_off, n_steps, want_traj=True, want_qp=True):
+        B = self.batch
+        x0 = f64(np.broadcast_to(f64(x0), (B, self.n_states)))
+        block_end = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(block_end), (B, np.atleast_2d(block_end).shape[1])), dtype=np.int32)
+        nb = block_end.shape[1]
+        block_off = f64(np.broadcast_to(f64(block_off).reshape(-1, nb, self.n_inputs), (B, nb, self.n_inputs)))
+        rec = 1 + self.n_states + 8
+        traj = np.zeros((B, n_steps, rec)) if want_traj else None
+        act = np.zeros((B, n_steps, self.n_controllers), dtype=np.uint32) if want_qp else None
+        obj = np.zeros((B, n_steps, self.n_controllers)) if want_qp else None
+        st = np.zeros((B, n_steps, self.n_controllers), dtype=np.int32) if want_qp else None
+        check(lib().cmpc_run_closed_loop(self._h, n_steps, ptr(x0), nb, ptr(block_end), ptr(block_off),
+                                         ptr(traj), ptr(act), ptr(obj), ptr(st)))
+        return dict(traj=traj, active=act, objective=obj, status=st)
+
+    def run_closed_loop_device(self, n_steps, x0_ptr, n_blocks, block_end_ptr, block_off_ptr, traj_ptr=0,
+                               act_ptr=0, obj_ptr=0, st_ptr=0, reinitialize=True, stream=0):
+        vp = lambda v: C.c_void_p(v) if v else None
+        check(lib().cmpc_run_closed_loop_device(self._h, n_steps, vp(x0_ptr), n_blocks, vp(block_end_ptr),
+                                                vp(block_off_ptr), vp(traj_ptr), vp(act_ptr), vp(obj_ptr),
+                                                vp(st_ptr), int(bool(reinitialize)), vp(stream)))
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(lib().cmpc_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- parity hooks ---------------------------------------------------------------------
+    def set_capture(self, on: bool = True):
+        check(lib().cmpc_set_capture(self._h, int(on)))
+
+    def linearization(self, ctrl: int):
+        B, n = self.batch, self.n_states
+        A = np.zeros((B, n, n)); Bd = np.zeros((B, n, 4)); f = np.zeros((B, n))
+        check(lib().cmpc_get_linearization(self._h, ctrl, ptr(A), ptr(Bd), ptr(f)))
+        return A, Bd, f
+
+    def qp(self, ctrl: int):
+        B, nv, nvo = self.batch, self.nv, self.nvo
+        H = np.zeros((B, nv, nv)); f = np.zeros((B, nv)); G = np.zeros((B, nv, max(nvo, 1)))
+        check(lib().cmpc_get_qp(self._h, ctrl, ptr(H), ptr(f), ptr(G)))
+        return H, f, (G if nvo else None)
+
+    def prediction(self, ctrl: int):
+        B, rows = self.batch, self.p * self.n_controlled_outputs[ctrl]
+        Su = np.zeros((B, rows, self.nv)); Suo = np.zeros((B, rows, max(self.nvo, 1)))
+        check(lib().cmpc_generate_prediction(self._h, ctrl, ptr(Su), ptr(Suo)))
+        return Su, (Suo if self.nvo else None)
+
+    def controller_state(self, ctrl: int):
+        B, n = self.batch, self.n_states
+        x = np.zeros((B, n)); dx = np.zeros((B, n + 84)); yo = np.zeros((B, 4)); uo = np.zeros((B, 4))
+        check(lib().cmpc_get_controller_state(self._h, ctrl, ptr(x), ptr(dx), ptr(yo), ptr(uo)))
+        return x, dx, yo, uo
+
+
+def from_setup(setup, batch: int = 1, p: int = 100, device: int = 0, n_solver_iterations=None) -> NerveCenter:
+    """Build a NerveCenter the way the reference driver does from a setup file."""
+    ic = InputConstraints(setup.lower, setup.upper, setup.rate_lower, setup.rate_upper)
+    nc = NerveCenter(setup.plant, setup.mode, batch=batch, p=p, device=device, constraints=ic,
+                     n_solver_iterations=n_solver_iterations if n_solver_iterations is not None else setup.n_iterations)
+    nc.SetWeights(setup.uwt, setup.ywt)
+    nc.SetOutputReference(np.asarray(setup.yref, dtype=np.float64))
+    return nc

@@ -1,0 +1,687 @@
+// C-ABI implementation (include/cmpc.h): handle, HBM layout, kernel launches.
+// There is deliberately no CPU path in this file: every compute entry point launches
+// sm_100a kernels and fails with CMPC_ERR_CUDA when that is not possible.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cmpc.h"
+#include "plant_kernels.cuh"
+#include "step_kernel.cuh"
+
+using namespace cmpc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(CMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+  return e;
+}
+
+}  // namespace
+
+struct cmpc_handle {
+  cmpc_config cfg;
+  int device = 0;
+  int shape = -1;  // index into the instantiated shapes
+  int N = 0, NIN = 0, NV = 0, NVO = 0, NCTRL = 0;
+  StepParams P;
+  DeviceState G;
+  double* d_yref = nullptr;
+  double *d_y = nullptr, *d_u = nullptr;  // [B][4]
+  double *d_xinit = nullptr, *d_uinit = nullptr, *d_uinitfull = nullptr, *d_yinit = nullptr;
+  // closed loop
+  double *d_x = nullptr, *d_ring = nullptr;
+  int* d_block_end = nullptr;
+  double* d_block_off = nullptr;
+  size_t block_cap = 0;
+  size_t smem_bytes = 0;
+  int64_t launches = 0;
+  bool initialized = false;
+  bool capture = false;
+  cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+// ---- shape dispatch ---------------------------------------------------------------------
+using ShapeCentPar = Shape<0, 3, 4, 1>;
+using ShapeCoopPar = Shape<0, 3, 2, 2>;
+using ShapeNcoopPar = Shape<0, 2, 2, 2>;
+using ShapeCentSer = Shape<1, 4, 4, 1>;
+using ShapeCoopSer = Shape<1, 4, 2, 2>;
+using ShapeNcoopSer = Shape<1, 2, 2, 2>;
+
+#define CMPC_DISPATCH(shape_id, FN, ...)                            \
+  switch (shape_id) {                                               \
+    case 0: return FN<ShapeCentPar>(__VA_ARGS__);                   \
+    case 1: return FN<ShapeCoopPar>(__VA_ARGS__);                   \
+    case 2: return FN<ShapeNcoopPar>(__VA_ARGS__);                  \
+    case 3: return FN<ShapeCentSer>(__VA_ARGS__);                   \
+    case 4: return FN<ShapeCoopSer>(__VA_ARGS__);                   \
+    case 5: return FN<ShapeNcoopSer>(__VA_ARGS__);                  \
+    default: return fail(CMPC_ERR_UNSUPPORTED, "unsupported shape"); \
+  }
+
+int find_shape(const cmpc_config& c) {
+  const int ny = c.n_controlled_outputs[0];
+  if (c.n_controllers == 2 && c.n_controlled_outputs[1] != ny) return -1;
+  struct Row { int plant, ny, nu, nctrl; };
+  const Row rows[6] = {{0, 3, 4, 1}, {0, 3, 2, 2}, {0, 2, 2, 2}, {1, 4, 4, 1}, {1, 4, 2, 2}, {1, 2, 2, 2}};
+  for (int i = 0; i < 6; ++i)
+    if (rows[i].plant == c.plant && rows[i].ny == ny && rows[i].nu == c.n_sub_control_inputs &&
+        rows[i].nctrl == c.n_controllers)
+      return i;
+  return -1;
+}
+
+template <class S>
+int shape_setup(cmpc_handle* h) {
+  const SmemLayout<S> lay(h->P.p, h->P.b_max);
+  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 2 * S::NCTRL * S::NV + 8);
+  if (h->smem_bytes > 227 * 1024)
+    return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
+  CU(cudaFuncSetAttribute(step_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          int(h->smem_bytes)));
+  return CMPC_OK;
+}
+
+template <class S>
+int launch_init(cmpc_handle* h, const double* x, const double* u, const double* uf, const double* y,
+                cudaStream_t st) {
+  const int B = h->cfg.batch;
+  init_kernel<S><<<(B + 127) / 128, 128, 0, st>>>(B, h->G, x, u, uf, y, h->P);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CMPC_OK;
+}
+
+template <class S>
+int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
+  step_kernel<S><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CMPC_OK;
+}
+
+template <class S>
+int launch_closed_loop(cmpc_handle* h, int n_steps, const double* x0, ClosedLoopArrays A,
+                       bool reinit, cudaStream_t st) {
+  const int B = h->cfg.batch;
+  const int blocks = (B + 63) / 64;
+  if (reinit) {
+    cl_start_kernel<S::PLANT><<<blocks, 64, 0, st>>>(B, x0, A, h->d_uinit, h->d_uinitfull);
+    h->launches++;
+    CU(cudaGetLastError());
+    int rc = launch_init<S>(h, A.x, h->d_uinit, h->d_uinitfull, A.y, st);
+    if (rc) return rc;
+    h->initialized = true;
+  }
+  double t = 0.0;
+  for (int k = 0; k < n_steps; ++k) {
+    int rc = launch_step<S>(h, A.y, A.u, st);
+    if (rc) return rc;
+    cl_advance_kernel<S::PLANT, S::NCTRL><<<blocks, 64, 0, st>>>(B, k, t, h->cfg.Ts, A, h->G.status,
+                                                                 h->G.active, h->G.objective);
+    h->launches++;
+    t += h->cfg.Ts;  // the reference driver accumulates t += Ts
+  }
+  CU(cudaGetLastError());
+  return CMPC_OK;
+}
+
+int check_handle(cmpc_handle* h) {
+  if (!h) return fail(CMPC_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  return CMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cmpc_last_error(void) { return g_err.c_str(); }
+
+int cmpc_plant_dims(int plant, int* n_states, int* n_inputs) {
+  if (plant != 0 && plant != 1) return fail(CMPC_ERR_ARG, "plant must be 0 or 1");
+  if (n_states) *n_states = plant == 0 ? 11 : 10;
+  if (n_inputs) *n_inputs = plant == 0 ? 9 : 8;
+  return CMPC_OK;
+}
+
+int cmpc_plant_defaults(int plant, double* x, double* u) {
+  if (plant != 0 && plant != 1) return fail(CMPC_ERR_ARG, "plant must be 0 or 1");
+  const double xp[11] = {0.916, 1.145, 0.152, 440, 0, 0.916, 1.145, 0.152, 440, 0, 1.12};
+  const double up[9] = {0.304, 0.43, 1.0, 0, 0.304, 0.43, 1.0, 0, 0.7};
+  const double xs[10] = {0.867, 1.03, 0.176, 395, 0, 0.999, 1.19, 0.176, 395, 0};
+  const double us[8] = {0.304, 0.405, 1, 0, 0.304, -1, 0.393, 0};
+  if (x) std::memcpy(x, plant == 0 ? xp : xs, sizeof(double) * (plant == 0 ? 11 : 10));
+  if (u) std::memcpy(u, plant == 0 ? up : us, sizeof(double) * (plant == 0 ? 9 : 8));
+  return CMPC_OK;
+}
+
+int cmpc_default_config(int plant, int mode, int batch, cmpc_config* cfg) {
+  if (!cfg) return fail(CMPC_ERR_ARG, "null cfg");
+  if ((plant != 0 && plant != 1) || mode < 0 || mode > 2) return fail(CMPC_ERR_ARG, "bad plant/mode");
+  std::memset(cfg, 0, sizeof *cfg);
+  cfg->plant = plant;
+  cfg->mode = mode;
+  cfg->p = 100;
+  cfg->m = 2;
+  cfg->Ts = 0.05;
+  cfg->batch = batch;
+  const int delays[4] = {0, 40, 0, 40};
+  std::memcpy(cfg->delays, delays, sizeof delays);
+  cfg->n_disturbance_states = 4;
+  const int id1[4] = {0, 1, 2, 3}, id2[4] = {2, 3, 0, 1};
+  std::memcpy(cfg->control_input_indices[0], id1, sizeof id1);
+  std::memcpy(cfg->control_input_indices[1], id2, sizeof id2);
+  auto set_out = [&](int c, std::initializer_list<int> o) {
+    cfg->n_controlled_outputs[c] = int(o.size());
+    int i = 0;
+    for (int v : o) cfg->controlled_output_indices[c][i++] = v;
+  };
+  if (mode == CMPC_MODE_CENTRALIZED) {
+    cfg->n_controllers = 1;
+    cfg->n_sub_control_inputs = 4;
+    cfg->n_iterations = 1;
+    if (plant == 0) set_out(0, {0, 1, 3}); else set_out(0, {0, 1, 2, 3});
+  } else {
+    cfg->n_controllers = 2;
+    cfg->n_sub_control_inputs = 2;
+    cfg->n_iterations = 9;
+    if (plant == 0 && mode == 1) { set_out(0, {0, 1, 3}); set_out(1, {0, 1, 3}); }
+    if (plant == 0 && mode == 2) { set_out(0, {0, 3}); set_out(1, {1, 3}); }
+    if (plant == 1 && mode == 1) { set_out(0, {0, 1, 2, 3}); set_out(1, {0, 1, 2, 3}); }
+    if (plant == 1 && mode == 2) { set_out(0, {0, 1}); set_out(1, {2, 3}); }
+  }
+  return CMPC_OK;
+}
+
+int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
+  if (!cfg || !out) return fail(CMPC_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->batch <= 0) return fail(CMPC_ERR_ARG, "batch must be positive");
+  if (cfg->m != 2) return fail(CMPC_ERR_UNSUPPORTED, "only move horizon m = 2 is built");
+  if (cfg->p < 2 || cfg->p > 256) return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon must be in [2, 256]");
+  const int delays[4] = {0, kDelay, 0, kDelay};
+  if (std::memcmp(cfg->delays, delays, sizeof delays) != 0 || cfg->n_disturbance_states != kNDist)
+    return fail(CMPC_ERR_UNSUPPORTED, "only Delays = {0,40,0,40} with 4 disturbance states is built");
+  if (cfg->n_iterations < 1) return fail(CMPC_ERR_ARG, "n_iterations must be >= 1");
+  const int shape = find_shape(*cfg);
+  if (shape < 0) return fail(CMPC_ERR_UNSUPPORTED, "no kernel instantiated for this controller shape");
+  for (int c = 0; c < cfg->n_controllers; ++c) {
+    unsigned seen = 0;
+    for (int i = 0; i < 4; ++i) {
+      const int v = cfg->control_input_indices[c][i];
+      if (v < 0 || v > 3) return fail(CMPC_ERR_ARG, "control_input_indices out of range");
+      seen |= 1u << v;
+      // delays are attached to the local position (aug_lin_sys.cc:160-173); the permutation
+      // must map delayed positions onto delayed plant inputs
+      if (delays[i] != delays[v]) return fail(CMPC_ERR_UNSUPPORTED, "permutation mixes delayed and undelayed inputs");
+    }
+    if (seen != 0xF) return fail(CMPC_ERR_ARG, "control_input_indices must be a permutation");
+    for (int i = 0; i < cfg->n_controlled_outputs[c]; ++i)
+      if (cfg->controlled_output_indices[c][i] < 0 || cfg->controlled_output_indices[c][i] > 3)
+        return fail(CMPC_ERR_ARG, "controlled_output_indices out of range");
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(CMPC_ERR_CUDA, "no CUDA device: the control step has no CPU path");
+  if (device < 0 || device >= n_dev) return fail(CMPC_ERR_ARG, "bad device index");
+  CU(cudaSetDevice(device));
+
+  cmpc_handle* h = new cmpc_handle;
+  h->cfg = *cfg;
+  h->device = device;
+  h->shape = shape;
+  cmpc_plant_dims(cfg->plant, &h->N, &h->NIN);
+  h->NCTRL = cfg->n_controllers;
+  h->NV = 2 * cfg->n_sub_control_inputs;
+  h->NVO = 2 * (4 - cfg->n_sub_control_inputs);
+  std::memset(&h->P, 0, sizeof h->P);
+  std::memset(&h->G, 0, sizeof h->G);
+  StepParams& P = h->P;
+  P.p = cfg->p;
+  P.b_max = (cfg->p + kBaby - 1) / kBaby;
+  int lg = 0;
+  while ((1 << lg) < P.b_max) ++lg;
+  P.n_pow = 3 + lg;
+  P.n_iter = cfg->n_iterations;
+  P.batch = cfg->batch;
+  P.Ts = cfg->Ts;
+  const int B = cfg->batch, NC = h->NCTRL, N = h->N;
+  for (int c = 0; c < NC; ++c) {
+    CtrlParams& cp = P.c[c];
+    const int ny = cfg->n_controlled_outputs[c], nu = cfg->n_sub_control_inputs;
+    for (int i = 0; i < 4; ++i) {
+      cp.out_idx[i] = i < ny ? cfg->controlled_output_indices[c][i] : 0;
+      cp.ctrl_idx[i] = cfg->control_input_indices[c][i];
+      cp.lower[i] = -1e30; cp.upper[i] = 1e30; cp.rate_lower[i] = -1e30; cp.rate_upper[i] = 1e30;
+    }
+    for (int i = 0; i < ny; ++i) cp.Q[i * ny + i] = 1.0;
+    for (int i = 0; i < nu; ++i) cp.R[i * nu + i] = 1.0;
+    for (int i = 0; i < 4; ++i) cp.M[(N + i) * 4 + i] = 1.0;  // default gain [0; I]
+  }
+  DeviceState& G = h->G;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(dalloc(&G.ctrl, size_t(B) * NC * kCtrlStateStride));
+  A(dalloc(&G.guess, size_t(B) * NC));
+  A(dalloc(&G.scen, size_t(B) * kScenStateStride));
+  A(dalloc(&G.u_offset, size_t(B) * h->NIN));
+  A(dalloc(&G.qpH, size_t(B) * NC * h->NV * h->NV));
+  A(dalloc(&G.qpf, size_t(B) * NC * h->NV));
+  A(dalloc(&G.qpG, size_t(B) * NC * h->NV * (h->NVO > 0 ? h->NVO : 1)));
+  A(dalloc(&G.status, size_t(B) * NC));
+  A(dalloc(&G.active, size_t(B) * NC));
+  A(dalloc(&G.objective, size_t(B) * NC));
+  A(dalloc(&h->d_yref, size_t(NC) * cfg->p * 4));
+  A(dalloc(&h->d_y, size_t(B) * 4));
+  A(dalloc(&h->d_u, size_t(B) * 4));
+  A(dalloc(&h->d_xinit, size_t(B) * N));
+  A(dalloc(&h->d_uinit, size_t(B) * 4));
+  A(dalloc(&h->d_uinitfull, size_t(B) * h->NIN));
+  A(dalloc(&h->d_yinit, size_t(B) * 4));
+  A(dalloc(&h->d_x, size_t(B) * N));
+  A(dalloc(&h->d_ring, size_t(B) * 2 * kDelay));
+  if (e != cudaSuccess) {
+    cmpc_destroy(h);
+    return fail(CMPC_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  P.yref = h->d_yref;
+  int rc = [&]() -> int { CMPC_DISPATCH(shape, shape_setup, h); }();
+  if (rc) {
+    cmpc_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return CMPC_OK;
+}
+
+int cmpc_destroy(cmpc_handle* h) {
+  if (!h) return CMPC_OK;
+  cudaSetDevice(h->device);
+  DeviceState& G = h->G;
+  void* ptrs[] = {G.ctrl, G.guess, G.scen, G.u_offset, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
+                  G.active, G.objective, h->d_yref, h->d_y, h->d_u, h->d_xinit, h->d_uinit,
+                  h->d_uinitfull, h->d_yinit, h->d_x, h->d_ring, h->d_block_end, h->d_block_off};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete h;
+  return CMPC_OK;
+}
+
+int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* ywt) {
+  if (int rc = check_handle(h)) return rc;
+  if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  CtrlParams& cp = h->P.c[ctrl];
+  const int ny = h->cfg.n_controlled_outputs[ctrl], nu = h->cfg.n_sub_control_inputs;
+  if (uwt) std::memcpy(cp.R, uwt, sizeof(double) * nu * nu);
+  if (ywt) std::memcpy(cp.Q, ywt, sizeof(double) * ny * ny);
+  return CMPC_OK;
+}
+
+int cmpc_set_output_reference(cmpc_handle* h, const double* yref) {
+  if (int rc = check_handle(h)) return rc;
+  if (!yref) return fail(CMPC_ERR_ARG, "null yref");
+  // nerve_center.h:237-249: each controller keeps its controlled outputs of every prediction row
+  const int p = h->cfg.p;
+  std::vector<double> sub(size_t(h->NCTRL) * p * 4, 0.0);
+  for (int c = 0; c < h->NCTRL; ++c) {
+    const int ny = h->cfg.n_controlled_outputs[c];
+    for (int r = 0; r < p; ++r)
+      for (int i = 0; i < ny; ++i)
+        sub[(size_t(c) * p + r) * ny + i] = yref[r * 4 + h->cfg.controlled_output_indices[c][i]];
+  }
+  // device layout [NCTRL][p][NY] with NY common to both controllers
+  const int ny = h->cfg.n_controlled_outputs[0];
+  std::vector<double> packed(size_t(h->NCTRL) * p * ny);
+  for (int c = 0; c < h->NCTRL; ++c)
+    for (int r = 0; r < p; ++r)
+      for (int i = 0; i < ny; ++i) packed[(size_t(c) * p + r) * ny + i] = sub[(size_t(c) * p + r) * ny + i];
+  CU(cudaMemcpy(h->d_yref, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return CMPC_OK;
+}
+
+int cmpc_set_constraints(cmpc_handle* h, int ctrl, const double* lower, const double* upper,
+                         const double* rate_lower, const double* rate_upper) {
+  if (int rc = check_handle(h)) return rc;
+  if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  if (!lower || !upper || !rate_lower || !rate_upper) return fail(CMPC_ERR_ARG, "null constraint array");
+  CtrlParams& cp = h->P.c[ctrl];
+  for (int i = 0; i < h->cfg.n_sub_control_inputs; ++i) {
+    cp.lower[i] = lower[i]; cp.upper[i] = upper[i];
+    cp.rate_lower[i] = rate_lower[i]; cp.rate_upper[i] = rate_upper[i];
+  }
+  return CMPC_OK;
+}
+
+int cmpc_set_observer_gain(cmpc_handle* h, int ctrl, const double* M) {
+  if (int rc = check_handle(h)) return rc;
+  if (ctrl < 0 || ctrl >= h->NCTRL || !M) return fail(CMPC_ERR_ARG, "bad argument");
+  std::memcpy(h->P.c[ctrl].M, M, sizeof(double) * (h->N + kNDist) * 4);
+  return CMPC_OK;
+}
+
+int cmpc_set_capture(cmpc_handle* h, int on) {
+  if (int rc = check_handle(h)) return rc;
+  const size_t B = h->cfg.batch, NC = h->NCTRL;
+  const size_t ny = h->cfg.n_controlled_outputs[0];
+  if (on && !h->G.lin) {
+    CU(dalloc(&h->G.lin, B * NC * (h->N * h->N + h->N * kNC)));
+    CU(dalloc(&h->G.etab, B * NC * size_t(h->cfg.p) * ny * kNC));
+  } else if (!on && h->G.lin) {
+    CU(cudaDeviceSynchronize());
+    cudaFree(h->G.lin); cudaFree(h->G.etab);
+    h->G.lin = nullptr; h->G.etab = nullptr;
+  }
+  h->capture = on != 0;
+  return CMPC_OK;
+}
+
+int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
+                    const double* u_init_full, const double* y_init) {
+  if (int rc = check_handle(h)) return rc;
+  if (!x_init || !u_init || !u_init_full || !y_init) return fail(CMPC_ERR_ARG, "null argument");
+  const size_t B = h->cfg.batch;
+  CU(cudaMemcpy(h->d_xinit, x_init, B * h->N * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_uinit, u_init, B * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_uinitfull, u_init_full, B * h->NIN * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_yinit, y_init, B * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = [&]() -> int {
+    CMPC_DISPATCH(h->shape, launch_init, h, h->d_xinit, h->d_uinit, h->d_uinitfull, h->d_yinit, nullptr);
+  }();
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  h->initialized = true;
+  return CMPC_OK;
+}
+
+int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_dev, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
+  if (!y_dev || !u_dev) return fail(CMPC_ERR_ARG, "null argument");
+  CMPC_DISPATCH(h->shape, launch_step, h, y_dev, u_dev, static_cast<cudaStream_t>(stream));
+}
+
+int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
+  if (int rc = check_handle(h)) return rc;
+  if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
+  if (!y || !u) return fail(CMPC_ERR_ARG, "null argument");
+  const size_t bytes = size_t(h->cfg.batch) * 4 * sizeof(double);
+  CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, nullptr));
+  int rc = [&]() -> int { CMPC_DISPATCH(h->shape, launch_step, h, h->d_y, h->d_u, nullptr); }();
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, nullptr));
+  CU(cudaStreamSynchronize(nullptr));
+  return CMPC_OK;
+}
+
+int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double* objective) {
+  if (int rc = check_handle(h)) return rc;
+  const size_t n = size_t(h->cfg.batch) * h->NCTRL;
+  CU(cudaDeviceSynchronize());
+  if (status) CU(cudaMemcpy(status, h->G.status, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (active) CU(cudaMemcpy(active, h->G.active, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  if (objective) CU(cudaMemcpy(objective, h->G.objective, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return CMPC_OK;
+}
+
+int cmpc_launch_count(cmpc_handle* h, int64_t* n) {
+  if (!h || !n) return fail(CMPC_ERR_ARG, "null argument");
+  *n = h->launches;
+  return CMPC_OK;
+}
+
+int cmpc_run_closed_loop_device(cmpc_handle* h, int n_steps, const double* x0_dev, int n_blocks,
+                                const int32_t* block_end_dev, const double* block_off_dev,
+                                double* traj_dev, uint32_t* qp_active_dev, double* qp_objective_dev,
+                                int32_t* qp_status_dev, int reinitialize, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (n_steps < 0 || n_blocks < 1 || !block_end_dev || !block_off_dev)
+    return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
+  if (reinitialize && !x0_dev) return fail(CMPC_ERR_ARG, "x0 required to (re)start the scenarios");
+  if (!reinitialize && !h->initialized) return fail(CMPC_ERR_STATE, "scenarios were never started");
+  ClosedLoopArrays A;
+  A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
+  A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;
+  A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
+  A.qp_status = qp_status_dev; A.n_steps = n_steps;
+  CMPC_DISPATCH(h->shape, launch_closed_loop, h, n_steps, x0_dev, A, reinitialize != 0,
+                static_cast<cudaStream_t>(stream));
+}
+
+int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
+                         const int32_t* block_end, const double* block_off, double* traj,
+                         uint32_t* qp_active, double* qp_objective, int32_t* qp_status) {
+  if (int rc = check_handle(h)) return rc;
+  if (!x0 || !block_end || !block_off || n_blocks < 1 || n_steps < 0)
+    return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
+  const size_t B = h->cfg.batch, NC = h->NCTRL, REC = 1 + h->N + 8;
+  double *d_traj = nullptr, *d_obj = nullptr;
+  unsigned* d_act = nullptr;
+  int* d_st = nullptr;
+  CU(cudaMemcpy(h->d_xinit, x0, B * h->N * sizeof(double), cudaMemcpyHostToDevice));
+  if (h->block_cap < B * n_blocks) {
+    if (h->d_block_end) cudaFree(h->d_block_end);
+    if (h->d_block_off) cudaFree(h->d_block_off);
+    CU(dalloc(&h->d_block_end, B * n_blocks));
+    CU(dalloc(&h->d_block_off, B * n_blocks * h->NIN));
+    h->block_cap = B * n_blocks;
+  }
+  CU(cudaMemcpy(h->d_block_end, block_end, B * n_blocks * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_block_off, block_off, B * n_blocks * h->NIN * sizeof(double), cudaMemcpyHostToDevice));
+  if (traj) CU(dalloc(&d_traj, B * n_steps * REC));
+  if (qp_active) CU(dalloc(&d_act, B * n_steps * NC));
+  if (qp_objective) CU(dalloc(&d_obj, B * n_steps * NC));
+  if (qp_status) CU(dalloc(&d_st, B * n_steps * NC));
+  int rc = cmpc_run_closed_loop_device(h, n_steps, h->d_xinit, n_blocks, h->d_block_end, h->d_block_off,
+                                       d_traj, d_act, d_obj, d_st, 1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc == CMPC_OK && e != cudaSuccess) rc = fail(CMPC_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == CMPC_OK) {
+    if (traj) cudaMemcpy(traj, d_traj, B * n_steps * REC * sizeof(double), cudaMemcpyDeviceToHost);
+    if (qp_active) cudaMemcpy(qp_active, d_act, B * n_steps * NC * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (qp_objective) cudaMemcpy(qp_objective, d_obj, B * n_steps * NC * sizeof(double), cudaMemcpyDeviceToHost);
+    if (qp_status) cudaMemcpy(qp_status, d_st, B * n_steps * NC * sizeof(int), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_traj); cudaFree(d_act); cudaFree(d_obj); cudaFree(d_st);
+  return rc;
+}
+
+// ---- parity hooks ---------------------------------------------------------------------
+int cmpc_get_linearization(cmpc_handle* h, int ctrl, double* Aorig, double* Bd, double* f) {
+  if (int rc = check_handle(h)) return rc;
+  if (!h->G.lin) return fail(CMPC_ERR_STATE, "enable cmpc_set_capture before the step");
+  if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  const int N = h->N, rec = N * N + N * kNC;
+  const size_t B = h->cfg.batch;
+  std::vector<double> buf(B * h->NCTRL * rec);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(buf.data(), h->G.lin, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (size_t b = 0; b < B; ++b) {
+    const double* r = buf.data() + (b * h->NCTRL + ctrl) * rec;
+    if (Aorig) std::memcpy(Aorig + b * N * N, r, sizeof(double) * N * N);
+    for (int i = 0; i < N; ++i) {
+      if (Bd) for (int c = 0; c < 4; ++c) Bd[(b * N + i) * 4 + c] = r[N * N + i * kNC + c];
+      if (f) f[b * N + i] = r[N * N + i * kNC + 4];
+    }
+  }
+  return CMPC_OK;
+}
+
+int cmpc_get_qp(cmpc_handle* h, int ctrl, double* H, double* f, double* Gx) {
+  if (int rc = check_handle(h)) return rc;
+  if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  const size_t B = h->cfg.batch, NC = h->NCTRL, NV = h->NV, NVO = h->NVO;
+  CU(cudaDeviceSynchronize());
+  if (H) CU(cudaMemcpy2D(H, NV * NV * sizeof(double), h->G.qpH + ctrl * NV * NV, NC * NV * NV * sizeof(double),
+                         NV * NV * sizeof(double), B, cudaMemcpyDeviceToHost));
+  if (f) CU(cudaMemcpy2D(f, NV * sizeof(double), h->G.qpf + ctrl * NV, NC * NV * sizeof(double),
+                         NV * sizeof(double), B, cudaMemcpyDeviceToHost));
+  if (Gx && NVO > 0)
+    CU(cudaMemcpy2D(Gx, NV * NVO * sizeof(double), h->G.qpG + ctrl * NV * NVO, NC * NV * NVO * sizeof(double),
+                    NV * NVO * sizeof(double), B, cudaMemcpyDeviceToHost));
+  return CMPC_OK;
+}
+
+int cmpc_generate_prediction(cmpc_handle* h, int ctrl, double* Su, double* Su_other) {
+  if (int rc = check_handle(h)) return rc;
+  if (!h->G.etab) return fail(CMPC_ERR_STATE, "enable cmpc_set_capture before the step");
+  if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  // Rebuild Su / Su_other from the impulse-response table exactly as GeneratePrediction
+  // accumulates them (aug_lin_sys.cc:311-328): Su[r, move0] = G_r, Su[r, move1] = sum_{k<r} G_k.
+  const size_t B = h->cfg.batch;
+  const int p = h->cfg.p, ny = h->cfg.n_controlled_outputs[0], nu = h->cfg.n_sub_control_inputs;
+  const int no = 4 - nu, NV = h->NV, NVO = h->NVO;
+  const size_t rec = size_t(p) * ny * kNC;
+  std::vector<double> E(B * h->NCTRL * rec);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(E.data(), h->G.etab, E.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (size_t b = 0; b < B; ++b) {
+    const double* e = E.data() + (b * h->NCTRL + ctrl) * rec;
+    std::vector<double> run(size_t(ny) * 4, 0.0);
+    for (int r = 0; r < p; ++r)
+      for (int y = 0; y < ny; ++y)
+        for (int i = 0; i < 4; ++i) {
+          const bool delayed = i & 1;
+          const int k = delayed ? r - kDelay : r;
+          const double gval = k >= 0 ? e[(size_t(k) * ny + y) * kNC + i] : 0.0;
+          const size_t row = b * size_t(p) * ny + size_t(r) * ny + y;
+          if (i < nu) {
+            if (Su) { Su[row * NV + i] = gval; Su[row * NV + nu + i] = run[y * 4 + i]; }
+          } else if (Su_other && NVO > 0) {
+            Su_other[row * NVO + (i - nu)] = gval;
+            Su_other[row * NVO + no + (i - nu)] = run[y * 4 + i];
+          }
+          run[y * 4 + i] += gval;
+        }
+  }
+  return CMPC_OK;
+}
+
+int cmpc_get_controller_state(cmpc_handle* h, int ctrl, double* x_hat, double* dx_aug, double* y_old,
+                              double* u_old) {
+  if (int rc = check_handle(h)) return rc;
+  if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  const size_t B = h->cfg.batch;
+  std::vector<double> buf(B * h->NCTRL * kCtrlStateStride);
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(buf.data(), h->G.ctrl, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const int N = h->N, NT = N + kNAug;
+  for (size_t b = 0; b < B; ++b) {
+    const double* r = buf.data() + (b * h->NCTRL + ctrl) * kCtrlStateStride;
+    if (x_hat) std::memcpy(x_hat + b * N, r + kOffXhat, sizeof(double) * N);
+    if (dx_aug) std::memcpy(dx_aug + b * NT, r + kOffDx, sizeof(double) * NT);
+    if (y_old) std::memcpy(y_old + b * 4, r + kOffYold, sizeof(double) * 4);
+    if (u_old) std::memcpy(u_old + b * 4, r + kOffUold, sizeof(double) * 4);
+  }
+  return CMPC_OK;
+}
+
+int cmpc_solve_qp(int device, int nq, int nv, const double* H, const double* f, const double* lb,
+                  const double* ub, const double* lbA, const double* ubA, uint32_t* guess_io, double* z,
+                  uint32_t* active, double* objective, int32_t* status) {
+  if (nq <= 0 || (nv != 4 && nv != 8)) return fail(CMPC_ERR_ARG, "nv must be 4 or 8");
+  if (!H || !f || !lb || !ub || !lbA || !ubA || !guess_io || !z || !active || !objective || !status)
+    return fail(CMPC_ERR_ARG, "null argument");
+  CU(cudaSetDevice(device));
+  double *dH, *df, *dlb, *dub, *dlbA, *dubA, *dz, *dobj;
+  unsigned *dg, *dact;
+  int* dst;
+  const size_t n = nq;
+  CU(dalloc(&dH, n * nv * nv)); CU(dalloc(&df, n * nv)); CU(dalloc(&dlb, n * nv)); CU(dalloc(&dub, n * nv));
+  CU(dalloc(&dlbA, n * nv)); CU(dalloc(&dubA, n * nv)); CU(dalloc(&dz, n * nv)); CU(dalloc(&dobj, n));
+  CU(dalloc(&dg, n)); CU(dalloc(&dact, n)); CU(dalloc(&dst, n));
+  CU(cudaMemcpy(dH, H, n * nv * nv * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(df, f, n * nv * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dlb, lb, n * nv * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dub, ub, n * nv * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dlbA, lbA, n * nv * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dubA, ubA, n * nv * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dg, guess_io, n * sizeof(unsigned), cudaMemcpyHostToDevice));
+  if (nv == 4)
+    qp_kernel<4><<<(nq + 63) / 64, 64>>>(nq, dH, df, dlb, dub, dlbA, dubA, dg, dz, dact, dobj, dst);
+  else
+    qp_kernel<8><<<(nq + 63) / 64, 64>>>(nq, dH, df, dlb, dub, dlbA, dubA, dg, dz, dact, dobj, dst);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(z, dz, n * nv * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(guess_io, dg, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(active, dact, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(objective, dobj, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(status, dst, n * sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dH); cudaFree(df); cudaFree(dlb); cudaFree(dub); cudaFree(dlbA); cudaFree(dubA);
+  cudaFree(dz); cudaFree(dobj); cudaFree(dg); cudaFree(dact); cudaFree(dst);
+  return CMPC_OK;
+}
+
+int cmpc_plant_eval(int device, int plant, int nq, const double* x, const double* u, double* dxdt,
+                    double* y, double* A, double* Bc, double* C) {
+  if ((plant != 0 && plant != 1) || nq <= 0 || !x || !u) return fail(CMPC_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(device));
+  const size_t n = nq, N = plant == 0 ? 11 : 10, NIN = plant == 0 ? 9 : 8;
+  double *dx, *du, *dd, *dy, *dA, *dB, *dC;
+  CU(dalloc(&dx, n * N)); CU(dalloc(&du, n * NIN)); CU(dalloc(&dd, n * N)); CU(dalloc(&dy, n * 4));
+  CU(dalloc(&dA, n * N * N)); CU(dalloc(&dB, n * N * 4)); CU(dalloc(&dC, n * 4 * N));
+  CU(cudaMemcpy(dx, x, n * N * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(du, u, n * NIN * sizeof(double), cudaMemcpyHostToDevice));
+  if (plant == 0)
+    plant_eval_kernel<0><<<(nq + 63) / 64, 64>>>(nq, dx, du, dd, dy, dA, dB, dC);
+  else
+    plant_eval_kernel<1><<<(nq + 63) / 64, 64>>>(nq, dx, du, dd, dy, dA, dB, dC);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  if (dxdt) CU(cudaMemcpy(dxdt, dd, n * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (y) CU(cudaMemcpy(y, dy, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (A) CU(cudaMemcpy(A, dA, n * N * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Bc) CU(cudaMemcpy(Bc, dB, n * N * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (C) CU(cudaMemcpy(C, dC, n * 4 * N * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(du); cudaFree(dd); cudaFree(dy); cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  return CMPC_OK;
+}
+
+int cmpc_plant_integrate(int device, int plant, int nq, double* x, const double* u, double Ts,
+                         int32_t* n_substeps) {
+  if ((plant != 0 && plant != 1) || nq <= 0 || !x || !u) return fail(CMPC_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(device));
+  const size_t n = nq, N = plant == 0 ? 11 : 10, NIN = plant == 0 ? 9 : 8;
+  double *dx, *du;
+  int* ds;
+  CU(dalloc(&dx, n * N)); CU(dalloc(&du, n * NIN)); CU(dalloc(&ds, n));
+  CU(cudaMemcpy(dx, x, n * N * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(du, u, n * NIN * sizeof(double), cudaMemcpyHostToDevice));
+  if (plant == 0)
+    plant_integrate_kernel<0><<<(nq + 63) / 64, 64>>>(nq, dx, du, Ts, ds);
+  else
+    plant_integrate_kernel<1><<<(nq + 63) / 64, 64>>>(nq, dx, du, Ts, ds);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(x, dx, n * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_substeps) CU(cudaMemcpy(n_substeps, ds, n * sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(du); cudaFree(ds);
+  return CMPC_OK;
+}
+
+}  // extern "C"

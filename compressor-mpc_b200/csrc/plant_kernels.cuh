@@ -1,0 +1,271 @@
+// Plant-side kernels of the closed loop: one GPU thread per scenario.
+//   SimulationSystem::{SetOffset,SetInput,operator(),Integrate}  include/simulation_system.h:66-116
+//   (Dormand-Prince 5(4) with odeint's controlled stepper, rel/abs 1e-6, error measured in the
+//    2-norm the reference installs at simulation_system.h:119-133)
+//   TimeDelay::GetDelayedInput                                     include/time_delay.h:41-58
+#pragma once
+#include <cuda_runtime.h>
+
+#include "plant_dev.cuh"
+#include "step_kernel.cuh"
+
+namespace cmpc {
+
+// One try_step of the controlled Dormand-Prince stepper (FSAL).  true: accepted.
+template <int PLANT>
+__device__ bool dopri5_try_step(const double* u, double* x, double* dxdt, double* t, double* dt) {
+  constexpr int N = PlantDims<PLANT>::N;
+  constexpr double b21 = 1.0 / 5;
+  constexpr double b31 = 3.0 / 40, b32 = 9.0 / 40;
+  constexpr double b41 = 44.0 / 45, b42 = -56.0 / 15, b43 = 32.0 / 9;
+  constexpr double b51 = 19372.0 / 6561, b52 = -25360.0 / 2187, b53 = 64448.0 / 6561, b54 = -212.0 / 729;
+  constexpr double b61 = 9017.0 / 3168, b62 = -355.0 / 33, b63 = 46732.0 / 5247, b64 = 49.0 / 176,
+                   b65 = -5103.0 / 18656;
+  constexpr double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+  constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                   dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+  const double h = *dt;
+  double k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], xt[N], xn[N];
+  const double* k1 = dxdt;
+#pragma unroll
+  for (int i = 0; i < N; ++i) xt[i] = x[i] + h * b21 * k1[i];
+  plant_derivative<PLANT>(xt, u, k2);
+#pragma unroll
+  for (int i = 0; i < N; ++i) xt[i] = x[i] + h * (b31 * k1[i] + b32 * k2[i]);
+  plant_derivative<PLANT>(xt, u, k3);
+#pragma unroll
+  for (int i = 0; i < N; ++i) xt[i] = x[i] + h * (b41 * k1[i] + b42 * k2[i] + b43 * k3[i]);
+  plant_derivative<PLANT>(xt, u, k4);
+#pragma unroll
+  for (int i = 0; i < N; ++i) xt[i] = x[i] + h * (b51 * k1[i] + b52 * k2[i] + b53 * k3[i] + b54 * k4[i]);
+  plant_derivative<PLANT>(xt, u, k5);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    xt[i] = x[i] + h * (b61 * k1[i] + b62 * k2[i] + b63 * k3[i] + b64 * k4[i] + b65 * k5[i]);
+  plant_derivative<PLANT>(xt, u, k6);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    xn[i] = x[i] + h * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
+  plant_derivative<PLANT>(xn, u, k7);
+  double sumsq = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double xerr = h * (dc1 * k1[i] + dc3 * k3[i] + dc4 * k4[i] + dc5 * k5[i] + dc6 * k6[i] + dc7 * k7[i]);
+    const double e = fabs(xerr) / (1e-6 + 1e-6 * (fabs(x[i]) + fabs(h) * fabs(k1[i])));
+    sumsq += e * e;
+  }
+  double err = sqrt(sumsq);
+  if (err > 1.0) {
+    *dt = h * fmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
+    return false;
+  }
+  *t += h;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    x[i] = xn[i];
+    dxdt[i] = k7[i];
+  }
+  if (err < 0.5) {
+    err = fmax(1.0 / 3125.0, err);
+    *dt = h * 9.0 / 10.0 * pow(err, -1.0 / 5.0);
+  }
+  return true;
+}
+
+// integrate_adaptive over [0, Ts] starting with dt = Ts; returns accepted steps (-1: stuck).
+template <int PLANT>
+__device__ int integrate_interval(const double* u, double* x, double Ts) {
+  constexpr int N = PlantDims<PLANT>::N;
+  double dxdt[N];
+  plant_derivative<PLANT>(x, u, dxdt);
+  double t = 0.0, dt = Ts;
+  int steps = 0, fails = 0;
+  const double eps = 2.220446049250313e-16;
+  while (Ts - t > eps) {
+    if ((t + dt) - Ts > eps) dt = Ts - t;
+    while (!dopri5_try_step<PLANT>(u, x, dxdt, &t, &dt)) {
+      if (++fails > 500) return -1;
+    }
+    fails = 0;
+    ++steps;
+  }
+  return steps;
+}
+
+struct ClosedLoopArrays {
+  double* x;           // [B][N] plant state
+  double* y;           // [B][4] measurement handed to the controller
+  double* u;           // [B][4] controller output
+  double* ring;        // [B][2][kDelay] actuator delay rings (plant side)
+  const int* block_end;     // [B][n_blocks]
+  const double* block_off;  // [B][n_blocks][NIN]
+  int n_blocks;
+  double* traj;        // [B][T][1+N+8] or null
+  unsigned* qp_active; // [B][T][NCTRL] or null
+  double* qp_objective;
+  int* qp_status;
+  int n_steps;
+};
+
+// Start of a closed-loop run: x = x0, y = GetOutput(x0), rings = 0.
+template <int PLANT>
+__global__ void cl_start_kernel(int B, const double* __restrict__ x0, ClosedLoopArrays A,
+                                double* u_init, double* u_init_full) {
+  constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[N], y[4];
+  for (int i = 0; i < N; ++i) {
+    x[i] = x0[size_t(b) * N + i];
+    A.x[size_t(b) * N + i] = x[i];
+  }
+  plant_output<PLANT>(x, y);
+  for (int i = 0; i < 4; ++i) {
+    A.y[size_t(b) * 4 + i] = y[i];
+    u_init[size_t(b) * 4 + i] = 0.0;
+  }
+  for (int i = 0; i < 2 * kDelay; ++i) A.ring[size_t(b) * 2 * kDelay + i] = 0.0;
+  constexpr double udef_par[9] = {0.304, 0.43, 1.0, 0, 0.304, 0.43, 1.0, 0, 0.7};
+  constexpr double udef_ser[8] = {0.304, 0.405, 1, 0, 0.304, -1, 0.393, 0};
+  for (int i = 0; i < NIN; ++i) u_init_full[size_t(b) * NIN + i] = PLANT == 0 ? udef_par[i] : udef_ser[i];
+}
+
+// After the control step of record k: write the record, push u through the delay rings,
+// integrate the plant over one sampling interval and produce the next measurement.
+template <int PLANT, int NCTRL>
+__global__ void cl_advance_kernel(int B, int k, double t_k, double Ts, ClosedLoopArrays A,
+                                  const int* __restrict__ status, const unsigned* __restrict__ active,
+                                  const double* __restrict__ objective) {
+  constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN, REC = 1 + N + 8;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[N], u[4], up[NIN];
+  for (int i = 0; i < N; ++i) x[i] = A.x[size_t(b) * N + i];
+  for (int i = 0; i < 4; ++i) u[i] = A.u[size_t(b) * 4 + i];
+  if (A.traj) {
+    double* r = A.traj + (size_t(b) * A.n_steps + k) * REC;
+    r[0] = t_k;
+    for (int i = 0; i < N; ++i) r[1 + i] = x[i];
+    for (int i = 0; i < 4; ++i) r[1 + N + i] = u[i];
+    for (int i = 0; i < 4; ++i) r[1 + N + 4 + i] = A.y[size_t(b) * 4 + i];
+  }
+  for (int c = 0; c < NCTRL; ++c) {
+    const size_t o = (size_t(b) * A.n_steps + k) * NCTRL + c;
+    if (A.qp_active) A.qp_active[o] = active[b * NCTRL + c];
+    if (A.qp_objective) A.qp_objective[o] = objective[b * NCTRL + c];
+    if (A.qp_status) A.qp_status[o] = status[b * NCTRL + c];
+  }
+  // plant-input offsets of the block this record belongs to (SetOffset)
+  int blk = 0;
+  while (blk + 1 < A.n_blocks && k >= A.block_end[b * A.n_blocks + blk]) ++blk;
+  constexpr double udef_par[9] = {0.304, 0.43, 1.0, 0, 0.304, 0.43, 1.0, 0, 0.7};
+  constexpr double udef_ser[8] = {0.304, 0.405, 1, 0, 0.304, -1, 0.393, 0};
+  for (int i = 0; i < NIN; ++i)
+    up[i] = (PLANT == 0 ? udef_par[i] : udef_ser[i]) + A.block_off[(size_t(b) * A.n_blocks + blk) * NIN + i];
+  // TimeDelay: inputs 1 and 3 come out 40 samples late
+  const int pos = k % kDelay;
+  double* ring = A.ring + size_t(b) * 2 * kDelay;
+  double ud[4] = {u[0], ring[pos], u[2], ring[kDelay + pos]};
+  ring[pos] = u[1];
+  ring[kDelay + pos] = u[3];
+  up[0] += ud[0]; up[3] += ud[1]; up[4] += ud[2]; up[7] += ud[3];
+  integrate_interval<PLANT>(up, x, Ts);
+  double y[4];
+  plant_output<PLANT>(x, y);
+  for (int i = 0; i < N; ++i) A.x[size_t(b) * N + i] = x[i];
+  for (int i = 0; i < 4; ++i) A.y[size_t(b) * 4 + i] = y[i];
+}
+
+// NerveCenter::Initialize + DistributedController::Initialize (nerve_center.h:98-104,186-203,
+// distributed_controller.cc:27-67): x_hat = x_init, dx_aug = 0, y_old = y_init, u_old = permuted
+// u_init, no QP warm start; NerveCenter's own u_old_/du_old_ start at zero (nerve_center.h:91-93).
+template <class S>
+__global__ void init_kernel(int B, DeviceState G, const double* __restrict__ x_init,
+                            const double* __restrict__ u_init, const double* __restrict__ u_init_full,
+                            const double* __restrict__ y_init, StepParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int c = 0; c < S::NCTRL; ++c) {
+    double* gs = G.ctrl + (size_t(b) * S::NCTRL + c) * kCtrlStateStride;
+    for (int i = 0; i < kCtrlStateStride; ++i) gs[i] = 0.0;
+    for (int i = 0; i < S::N; ++i) gs[kOffXhat + i] = x_init[size_t(b) * S::N + i];
+    for (int i = 0; i < 4; ++i) {
+      gs[kOffYold + i] = y_init[size_t(b) * 4 + i];
+      gs[kOffUold + i] = u_init[size_t(b) * 4 + P.c[c].ctrl_idx[i]];
+    }
+    G.guess[size_t(b) * S::NCTRL + c] = kQpNoGuess;
+    G.status[size_t(b) * S::NCTRL + c] = 0;
+    G.active[size_t(b) * S::NCTRL + c] = 0;
+    G.objective[size_t(b) * S::NCTRL + c] = 0.0;
+  }
+  for (int i = 0; i < kScenStateStride; ++i) G.scen[size_t(b) * kScenStateStride + i] = 0.0;
+  for (int i = 0; i < S::NIN; ++i) G.u_offset[size_t(b) * S::NIN + i] = u_init_full[size_t(b) * S::NIN + i];
+}
+
+// Stand-alone plant evaluation / integration / QP kernels behind the parity hooks.
+template <int PLANT>
+__global__ void plant_eval_kernel(int nq, const double* __restrict__ x, const double* __restrict__ u,
+                                  double* dxdt, double* y, double* A, double* Bc, double* C) {
+  constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nq) return;
+  double xl[N], ul[NIN], Al[N * N], Bl[N * 4], Cl[4 * N], fl[N], yl[4];
+  for (int i = 0; i < N; ++i) xl[i] = x[size_t(b) * N + i];
+  for (int i = 0; i < NIN; ++i) ul[i] = u[size_t(b) * NIN + i];
+  plant_linearize<PLANT>(xl, ul, Al, Bl, Cl, fl);
+  plant_output<PLANT>(xl, yl);
+  if (dxdt) for (int i = 0; i < N; ++i) dxdt[size_t(b) * N + i] = fl[i];
+  if (y) for (int i = 0; i < 4; ++i) y[size_t(b) * 4 + i] = yl[i];
+  if (A) for (int i = 0; i < N * N; ++i) A[size_t(b) * N * N + i] = Al[i];
+  if (Bc) for (int i = 0; i < N * 4; ++i) Bc[size_t(b) * N * 4 + i] = Bl[i];
+  if (C) for (int i = 0; i < 4 * N; ++i) C[size_t(b) * 4 * N + i] = Cl[i];
+}
+
+template <int PLANT>
+__global__ void plant_integrate_kernel(int nq, double* x, const double* __restrict__ u, double Ts,
+                                       int* n_substeps) {
+  constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nq) return;
+  double xl[N], ul[NIN];
+  for (int i = 0; i < N; ++i) xl[i] = x[size_t(b) * N + i];
+  for (int i = 0; i < NIN; ++i) ul[i] = u[size_t(b) * NIN + i];
+  const int s = integrate_interval<PLANT>(ul, xl, Ts);
+  for (int i = 0; i < N; ++i) x[size_t(b) * N + i] = xl[i];
+  if (n_substeps) n_substeps[b] = s;
+}
+
+template <int NV>
+__global__ void qp_kernel(int nq, const double* __restrict__ H, const double* __restrict__ f,
+                          const double* __restrict__ lb, const double* __restrict__ ub,
+                          const double* __restrict__ lbA, const double* __restrict__ ubA,
+                          unsigned* guess_io, double* z, unsigned* active, double* objective,
+                          int* status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nq) return;
+  QpData<NV> qd;
+  double Hl[NV * NV], fl[NV], zl[NV];
+  for (int i = 0; i < NV * NV; ++i) Hl[i] = H[size_t(b) * NV * NV + i];
+  for (int i = 0; i < NV; ++i) {
+    fl[i] = f[size_t(b) * NV + i];
+    qd.lb[i] = lb[size_t(b) * NV + i];
+    qd.ub[i] = ub[size_t(b) * NV + i];
+    qd.lbA[i] = lbA[size_t(b) * NV + i];
+    qd.ubA[i] = ubA[size_t(b) * NV + i];
+  }
+  unsigned g = guess_io[b], act = 0;
+  double obj = 0.0;
+  int st = 3;
+  if (qp_invert_spd<NV>(Hl, qd.J)) {
+    st = qp_solve<NV, NV / 2>(qd, Hl, fl, &g, zl, &act, &obj);
+  } else {
+    for (int i = 0; i < NV; ++i) zl[i] = 0.0;
+  }
+  for (int i = 0; i < NV; ++i) z[size_t(b) * NV + i] = zl[i];
+  guess_io[b] = g;
+  active[b] = act;
+  objective[b] = obj;
+  status[b] = st;
+}
+
+}  // namespace cmpc

@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): applied inputs and QP objective within 1e-6 relative
+(floor 1e-9 absolute) over a closed-loop run, identical optimal active sets.  Intermediate
+quantities (Jacobians, H, f) are held to much tighter bounds because both sides compute in FP64.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import CASES
+
+pytestmark = pytest.mark.gpu
+
+RTOL_U = 1e-6
+ATOL_U = 1e-9
+
+
+def rel_err(a, b, floor):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+@pytest.mark.parametrize("plant", [0, 1])
+def test_plant_eval_matches_oracle(plant, pkg, gpu_lib):
+    x0, u0 = ol.plant_defaults(plant)
+    rng = np.random.default_rng(1)
+    nq = 64
+    X = x0 * (1 + 0.02 * rng.uniform(-1, 1, (nq, len(x0))))
+    U = u0 + 0.05 * rng.uniform(-1, 1, (nq, len(u0)))
+    idx_rec = [3, 7]
+    U[:, idx_rec] = np.abs(U[:, idx_rec])         # recycle valves >= 0
+    U[: nq // 4, 3] = 0.005                        # inside the smoothed dead zone (compressor.cc:154-164)
+    U[nq // 4: nq // 2, 3] = 0.015
+    X[0], U[0] = x0, u0
+    out = pkg.capi.plant_eval(plant, X, U)
+    for b in range(nq):
+        A, B, C, f = ol.plant_linearize(plant, X[b], U[b])
+        assert np.allclose(out["dxdt"][b], ol.plant_derivative(plant, X[b], U[b]), rtol=1e-9, atol=1e-12)
+        assert np.allclose(out["y"][b], ol.plant_output(plant, X[b]), rtol=1e-13)
+        assert np.allclose(out["A"][b], A, rtol=1e-9, atol=1e-12)
+        assert np.allclose(out["B"][b], B, rtol=1e-11, atol=1e-15)
+        assert np.allclose(out["C"][b], C, rtol=1e-13)
+
+
+@pytest.mark.parametrize("plant", [0, 1])
+def test_plant_integrate_matches_oracle(plant, pkg, gpu_lib):
+    x0, u0 = ol.plant_defaults(plant)
+    rng = np.random.default_rng(2)
+    nq = 32
+    X = x0 * (1 + 0.02 * rng.uniform(-1, 1, (nq, len(x0))))
+    U = np.tile(u0, (nq, 1))
+    U[:, 0] += 0.05 * rng.uniform(-1, 1, nq)
+    U[:, -1] += -0.3 * rng.uniform(0, 1, nq)
+    Xg, steps = pkg.capi.plant_integrate(plant, X, U)
+    for b in range(nq):
+        xo, so = ol.plant_integrate(plant, X[b], U[b])
+        assert so == steps[b]
+        assert np.allclose(Xg[b], xo, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("nv", [4, 8])
+def test_qp_solver_matches_oracle(nv, pkg, gpu_lib):
+    rng = np.random.default_rng(3)
+    nq, nu = 256, nv // 2
+    H = np.zeros((nq, nv, nv)); f = np.zeros((nq, nv))
+    lb = np.zeros((nq, nv)); ub = np.zeros((nq, nv)); lbA = np.zeros((nq, nv)); ubA = np.zeros((nq, nv))
+    for q in range(nq):
+        M = rng.standard_normal((nv, nv))
+        H[q] = M @ M.T + 0.3 * np.eye(nv)
+        f[q] = rng.standard_normal(nv) * rng.choice([0.1, 1.0, 5.0])
+        lb[q] = -rng.uniform(0.05, 1, nv); ub[q] = rng.uniform(0.05, 1, nv)
+        lbA[q] = -rng.uniform(0.05, 0.5, nv); ubA[q] = rng.uniform(0.05, 0.5, nv)
+    g = pkg.capi.solve_qp(H, f, lb, ub, lbA, ubA)
+    n_active = 0
+    for q in range(nq):
+        r = ol.solve_qp(H[q], f[q], lb[q], ub[q], lbA[q], ubA[q], nu)
+        assert g["status"][q] == r["status"] == 0
+        assert np.allclose(g["z"][q], r["z"], rtol=1e-9, atol=1e-12)
+        assert g["active"][q] == r["active"], (q, bin(g["active"][q]), bin(r["active"]))
+        assert np.isclose(g["objective"][q], r["objective"], rtol=1e-9, atol=1e-12)
+        n_active += bin(r["active"]).count("1")
+    assert n_active > nq  # the random problems do exercise the constraints
+    # warm start from the optimal working sets gives the same answers
+    g2 = pkg.capi.solve_qp(H, f, lb, ub, lbA, ubA, guess=g["working_set"])
+    assert np.allclose(g2["z"], g["z"], rtol=1e-12, atol=1e-14) and (g2["active"] == g["active"]).all()
+
+
+def _oracle_drive(setup, x0, u_def, n_steps, p=100):
+    """Run the oracle closed loop and return the measurement sequence it saw."""
+    o = ol.Oracle(setup, p=p)
+    out = o.run_closed_loop(x0, setup.block_end_records(n_steps=n_steps), setup.sim_offsets, n_steps)
+    n = len(x0)
+    return out["traj"][0][:, 5 + n:]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_control_step_matches_oracle(case, setups, pkg, gpu_lib):
+    """Step-by-step: same y sequence into both controllers, compare QP data, inputs and state."""
+    s = setups[case]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    T = 60
+    ys = _oracle_drive(s, x_def, u_def, T)
+    ys[45:] *= 1.0 + 2e-3  # a measurement jump the controller has not seen coming
+    nc = pkg.from_setup(s, batch=2)
+    nc.set_capture(True)
+    o = ol.Oracle(s)
+    y0 = ol.plant_output(s.plant, x_def)
+    nc.Initialize(x_def, np.zeros(4), u_def, y0)
+    o.initialize(x_def, np.zeros(4), u_def, y0)
+    for k in range(T):
+        ug = nc.GetNextInput(ys[k])
+        uo = o.get_next_input(ys[k])
+        assert np.array_equal(ug[0], ug[1])
+        assert rel_err(ug[0], uo, 1e-9 / RTOL_U) < RTOL_U, (k, ug[0], uo)
+        info = nc.step_info()
+        for c in range(nc.n_controllers):
+            Hg, fg, Gg = nc.qp(c)
+            Ho, fo = o.qp(c)
+            assert np.allclose(Hg[0], Ho, rtol=1e-10, atol=1e-9), (k, c)
+            assert np.allclose(fg[0], fo, rtol=1e-8, atol=1e-9 * np.abs(fo).max()), (k, c, fg[0], fo)
+            Ag, Bg, fdg = nc.linearization(c)
+            Ao, Bo, Ado, Co, fdo = o.linearization(c)
+            assert np.allclose(Ag[0], Ao, rtol=1e-11, atol=1e-14)
+            assert np.allclose(fdg[0], fdo, rtol=1e-10, atol=1e-15)
+            Sug, Suog = nc.prediction(c)
+            Suo_, _, _, Suoo = o.prediction(c)
+            assert np.allclose(Sug[0], Suo_, rtol=1e-9, atol=1e-12), (k, c)
+            if Suog is not None:
+                assert np.allclose(Suog[0], Suoo, rtol=1e-9, atol=1e-12)
+                # cross term: f_it = f + Gx du_other  <=>  Gx = (Q Su)' Su_other
+                ny = nc.n_controlled_outputs[c]
+                Q = np.kron(np.eye(nc.p), np.asarray(s.ywt[c]))
+                assert np.allclose(Gg[0], (Q @ Suo_).T @ Suoo, rtol=1e-9, atol=1e-9)
+            xg, dxg, yog, uog = nc.controller_state(c)
+            xo, dxo, yoo, uoo = o.ctrl_state(c)
+            assert np.allclose(xg[0], xo, rtol=1e-12, atol=1e-14)
+            assert np.allclose(dxg[0], dxo, rtol=1e-9, atol=1e-13)
+            assert np.allclose(uog[0], uoo, rtol=1e-8, atol=1e-13)
+            st, act, obj = o.last_qp_info(c)
+            assert info["status"][0, c] == st == 0
+            assert info["active"][0, c] == act, (k, c, bin(info["active"][0, c]), bin(act))
+            assert np.isclose(info["objective"][0, c], obj, rtol=RTOL_U, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_closed_loop_matches_oracle(case, setups, pkg, gpu_lib):
+    """Perturbed scenarios through the on-device closed loop vs the oracle's closed loop."""
+    s = setups[case]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 6, 400
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = np.minimum(be[:, 0], 150 + 20 * np.arange(B))   # pull the disturbance into the window
+    nc = pkg.from_setup(s, batch=B)
+    g = nc.run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s).run_closed_loop(x0, be, bo, T, n_threads=4)
+    n = len(x_def)
+    ug, uo = g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n]
+    assert rel_err(ug, uo, ATOL_U / RTOL_U) < RTOL_U
+    assert rel_err(g["traj"][:, :, 1:1 + n], o["traj"][:, :, 1:1 + n], 1e-3) < 1e-8
+    assert (g["status"] == 0).all() and (o["status"] == 0).all()
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+    assert np.array_equal(g["traj"][:, :, 0], o["traj"][:, :, 0])
+    assert (g["active"] != 0).any()
+
+
+def test_scenario0_reproduces_reference_records(setups, golden, pkg, gpu_lib):
+    """GPU closed loop, nominal scenario, against the reference's recorded coop9.dat run."""
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    T = 1600
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, 2, T)
+    g = pkg.from_setup(s, batch=2).run_closed_loop(x0, be, bo, T)
+    idx = golden["coop-par/index"]; rec = golden["coop-par/records"]
+    keep = idx < T
+    tr = g["traj"][0][idx[keep]]
+    n = len(x_def)
+    assert (np.abs(tr[:, 1:1 + n] - rec[keep, 1:1 + n]) / np.maximum(np.abs(rec[keep, 1:1 + n]), 1e-3)).max() < 1e-5
+    assert np.abs(tr[:, 1 + n:5 + n] - rec[keep, 1 + n:5 + n]).max() < 5e-6
+
+
+def test_constraint_stress_matches_oracle(setups, pkg, gpu_lib):
+    """Tight rate limits and a large disturbance: rate rows and bounds become active, the working
+    set changes often (the reference's goldens never exercise this)."""
+    import copy
+    s = copy.deepcopy(setups["coop-par"])
+    s.rate_lower = np.array([-2e-3, -2e-3]); s.rate_upper = np.array([2e-3, 2e-3])
+    s.upper = np.array([0.05, 0.2])
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 4, 300
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 40
+    bo[:, 1, 8] = -0.45
+    g = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s).run_closed_loop(x0, be, bo, T, n_threads=4)
+    n = len(x_def)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    rate_bits = 0xFF00
+    assert (g["active"] & rate_bits).any(), "rate constraints never became active"
+    assert len(np.unique(g["active"])) > 3
