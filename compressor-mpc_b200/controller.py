@@ -109,6 +109,10 @@ class NerveCenter:
         check(lib().cmpc_get_next_input(self._h, ptr(y), ptr(u)))
         return u
 
+    def GetNextInputRaw(self, y_host_ptr: int, u_host_ptr: int):
+        """Same call on raw host addresses (e.g. pinned torch tensors): B x 4 doubles each."""
+        check(lib().cmpc_get_next_input(self._h, C.c_void_p(y_host_ptr), C.c_void_p(u_host_ptr)))
+
     def GetNextInputDevice(self, y_dev_ptr: int, u_dev_ptr: int, stream: int = 0):
         check(lib().cmpc_get_next_input_device(self._h, C.c_void_p(y_dev_ptr), C.c_void_p(u_dev_ptr),
                                                C.c_void_p(stream)))
@@ -136,12 +140,21 @@ class NerveCenter:
                                          ptr(traj), ptr(act), ptr(obj), ptr(st)))
         return dict(traj=traj, active=act, objective=obj, status=st)
 
-    def run_closed_loop_device(self, n_steps, x0_ptr, n_blocks, block_end_ptr, block_off_ptr, traj_ptr=0,
-                               act_ptr=0, obj_ptr=0, st_ptr=0, reinitialize=True, stream=0):
+    def run_closed_loop_device(self, first_step, n_steps, total_steps, x0_ptr, n_blocks, block_end_ptr,
+                               block_off_ptr, traj_ptr=0, act_ptr=0, obj_ptr=0, st_ptr=0, stream=0):
+        """Device-resident closed loop (raw device addresses, e.g. torch.Tensor.data_ptr())."""
         vp = lambda v: C.c_void_p(v) if v else None
-        check(lib().cmpc_run_closed_loop_device(self._h, n_steps, vp(x0_ptr), n_blocks, vp(block_end_ptr),
-                                                vp(block_off_ptr), vp(traj_ptr), vp(act_ptr), vp(obj_ptr),
-                                                vp(st_ptr), int(bool(reinitialize)), vp(stream)))
+        check(lib().cmpc_run_closed_loop_device(self._h, first_step, n_steps, total_steps, vp(x0_ptr), n_blocks,
+                                                vp(block_end_ptr), vp(block_off_ptr), vp(traj_ptr),
+                                                vp(act_ptr), vp(obj_ptr), vp(st_ptr), vp(stream)))
+
+    def set_timing(self, on: bool = True):
+        check(lib().cmpc_set_timing(self._h, int(on)))
+
+    def get_timing(self):
+        n = C.c_int64(); ms = C.c_double()
+        check(lib().cmpc_get_timing(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -59,7 +59,9 @@ struct cmpc_handle {
   int64_t launches = 0;
   bool initialized = false;
   bool capture = false;
-  cudaStream_t stream = nullptr;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop) around control-step launches
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -118,15 +120,27 @@ int launch_init(cmpc_handle* h, const double* x, const double* u, const double* 
 
 template <class S>
 int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
+  if (h->timing) {
+    if (h->ev_used + 2 > h->ev.size()) {
+      const size_t old = h->ev.size();
+      h->ev.resize(old + 512);
+      for (size_t i = old; i < h->ev.size(); ++i) CU(cudaEventCreate(&h->ev[i]));
+    }
+    CU(cudaEventRecord(h->ev[h->ev_used], st));
+  }
   step_kernel<S><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
   h->launches++;
+  if (h->timing) {
+    CU(cudaEventRecord(h->ev[h->ev_used + 1], st));
+    h->ev_used += 2;
+  }
   CU(cudaGetLastError());
   return CMPC_OK;
 }
 
 template <class S>
-int launch_closed_loop(cmpc_handle* h, int n_steps, const double* x0, ClosedLoopArrays A,
-                       bool reinit, cudaStream_t st) {
+int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double* x0,
+                       ClosedLoopArrays A, bool reinit, cudaStream_t st) {
   const int B = h->cfg.batch;
   const int blocks = (B + 63) / 64;
   if (reinit) {
@@ -138,7 +152,8 @@ int launch_closed_loop(cmpc_handle* h, int n_steps, const double* x0, ClosedLoop
     h->initialized = true;
   }
   double t = 0.0;
-  for (int k = 0; k < n_steps; ++k) {
+  for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;
+  for (int k = first_step; k < first_step + n_steps; ++k) {
     int rc = launch_step<S>(h, A.y, A.u, st);
     if (rc) return rc;
     cl_advance_kernel<S::PLANT, S::NCTRL><<<blocks, 64, 0, st>>>(B, k, t, h->cfg.Ts, A, h->G.status,
@@ -328,6 +343,7 @@ int cmpc_destroy(cmpc_handle* h) {
                   h->d_uinitfull, h->d_yinit, h->d_x, h->d_ring, h->d_block_end, h->d_block_off};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return CMPC_OK;
 }
@@ -454,22 +470,46 @@ int cmpc_launch_count(cmpc_handle* h, int64_t* n) {
   return CMPC_OK;
 }
 
-int cmpc_run_closed_loop_device(cmpc_handle* h, int n_steps, const double* x0_dev, int n_blocks,
-                                const int32_t* block_end_dev, const double* block_off_dev,
-                                double* traj_dev, uint32_t* qp_active_dev, double* qp_objective_dev,
-                                int32_t* qp_status_dev, int reinitialize, void* stream) {
+int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int total_steps,
+                                const double* x0_dev, int n_blocks, const int32_t* block_end_dev,
+                                const double* block_off_dev, double* traj_dev, uint32_t* qp_active_dev,
+                                double* qp_objective_dev, int32_t* qp_status_dev, void* stream) {
   if (int rc = check_handle(h)) return rc;
-  if (n_steps < 0 || n_blocks < 1 || !block_end_dev || !block_off_dev)
+  if (first_step < 0 || n_steps < 0 || first_step + n_steps > total_steps || n_blocks < 1 ||
+      !block_end_dev || !block_off_dev)
     return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
-  if (reinitialize && !x0_dev) return fail(CMPC_ERR_ARG, "x0 required to (re)start the scenarios");
-  if (!reinitialize && !h->initialized) return fail(CMPC_ERR_STATE, "scenarios were never started");
+  const bool reinit = first_step == 0;
+  if (reinit && !x0_dev) return fail(CMPC_ERR_ARG, "x0 required to start the scenarios");
+  if (!reinit && !h->initialized) return fail(CMPC_ERR_STATE, "scenarios were never started");
   ClosedLoopArrays A;
   A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
   A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;
   A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
-  A.qp_status = qp_status_dev; A.n_steps = n_steps;
-  CMPC_DISPATCH(h->shape, launch_closed_loop, h, n_steps, x0_dev, A, reinitialize != 0,
+  A.qp_status = qp_status_dev; A.n_steps = total_steps;
+  CMPC_DISPATCH(h->shape, launch_closed_loop, h, first_step, n_steps, x0_dev, A, reinit,
                 static_cast<cudaStream_t>(stream));
+}
+
+int cmpc_set_timing(cmpc_handle* h, int on) {
+  if (int rc = check_handle(h)) return rc;
+  h->timing = on != 0;
+  h->ev_used = 0;
+  return CMPC_OK;
+}
+
+int cmpc_get_timing(cmpc_handle* h, int64_t* n_step_launches, double* step_kernel_ms) {
+  if (int rc = check_handle(h)) return rc;
+  CU(cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    total += ms;
+  }
+  if (n_step_launches) *n_step_launches = int64_t(h->ev_used / 2);
+  if (step_kernel_ms) *step_kernel_ms = total;
+  h->ev_used = 0;
+  return CMPC_OK;
 }
 
 int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
@@ -496,8 +536,8 @@ int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_bl
   if (qp_active) CU(dalloc(&d_act, B * n_steps * NC));
   if (qp_objective) CU(dalloc(&d_obj, B * n_steps * NC));
   if (qp_status) CU(dalloc(&d_st, B * n_steps * NC));
-  int rc = cmpc_run_closed_loop_device(h, n_steps, h->d_xinit, n_blocks, h->d_block_end, h->d_block_off,
-                                       d_traj, d_act, d_obj, d_st, 1, nullptr);
+  int rc = cmpc_run_closed_loop_device(h, 0, n_steps, n_steps, h->d_xinit, n_blocks, h->d_block_end,
+                                       h->d_block_off, d_traj, d_act, d_obj, d_st, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc == CMPC_OK && e != cudaSuccess) rc = fail(CMPC_ERR_CUDA, cudaGetErrorString(e));
   if (rc == CMPC_OK) {

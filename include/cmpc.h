@@ -112,12 +112,19 @@ int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_bl
                          const int32_t* block_end, const double* block_off, double* traj,
                          uint32_t* qp_active, double* qp_objective, int32_t* qp_status);
 /* Device-resident variant: same arrays in device memory, runs on `stream`, no sync.
- * If reinitialize != 0 the scenarios are (re)started from x0 first. */
-int cmpc_run_closed_loop_device(cmpc_handle* h, int n_steps, const double* x0_dev, int n_blocks,
-                                const int32_t* block_end_dev, const double* block_off_dev,
-                                double* traj_dev, uint32_t* qp_active_dev,
-                                double* qp_objective_dev, int32_t* qp_status_dev,
-                                int reinitialize, void* stream);
+ * Runs records [first_step, first_step + n_steps) of a run whose arrays hold total_steps
+ * records per scenario; first_step == 0 (re)starts the scenarios from x0_dev, later calls
+ * continue from the state the handle holds. */
+int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int total_steps,
+                                const double* x0_dev, int n_blocks, const int32_t* block_end_dev,
+                                const double* block_off_dev, double* traj_dev,
+                                uint32_t* qp_active_dev, double* qp_objective_dev,
+                                int32_t* qp_status_dev, void* stream);
+/* Per-kernel device timing: when on, every control-step kernel launch is bracketed by CUDA
+ * events on its stream; cmpc_get_timing synchronises, returns the number of timed launches and
+ * their summed duration, and resets the counters. */
+int cmpc_set_timing(cmpc_handle* h, int on);
+int cmpc_get_timing(cmpc_handle* h, int64_t* n_step_launches, double* step_kernel_ms);
 /* Number of kernel launches issued by this handle so far (for bench accounting). */
 int cmpc_launch_count(cmpc_handle* h, int64_t* n_launches);
 
