@@ -99,8 +99,8 @@ int find_shape(const cmpc_config& c) {
 
 template <class S>
 int shape_setup(cmpc_handle* h) {
-  const SmemLayout<S> lay(h->P.p, h->P.b_max);
-  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 2 * S::NCTRL * S::NV + 8);
+  const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow);
+  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + S::NCTRL * S::NV + 8);
   if (h->smem_bytes > 227 * 1024)
     return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
   CU(cudaFuncSetAttribute(step_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -353,6 +353,11 @@ int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* 
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   CtrlParams& cp = h->P.c[ctrl];
   const int ny = h->cfg.n_controlled_outputs[ctrl], nu = h->cfg.n_sub_control_inputs;
+  if (ywt)
+    for (int i = 0; i < ny; ++i)
+      for (int j = 0; j < i; ++j)
+        if (ywt[i * ny + j] != ywt[j * ny + i])
+          return fail(CMPC_ERR_UNSUPPORTED, "ywt must be symmetric (H = Su' Q Su is kept as a symmetric matrix)");
   if (uwt) std::memcpy(cp.R, uwt, sizeof(double) * nu * nu);
   if (ywt) std::memcpy(cp.Q, ywt, sizeof(double) * ny * ny);
   return CMPC_OK;

@@ -38,7 +38,7 @@ constexpr int kBaby = 8;        // baby steps a = 0..7
 constexpr int kNC = 5;          // columns of [Bd | fd]
 constexpr int kCtrlStateStride = 128;  // doubles per (scenario, controller) in global memory
 constexpr int kScenStateStride = 16;   // doubles per scenario
-constexpr int kMaxPow = 8;      // Ad^(2^j), j = 0..7
+constexpr int kMaxRows = 4;     // prediction rows owned by one thread (p <= 4 * TPC)
 
 // offsets inside one controller's global state record
 constexpr int kOffXhat = 0, kOffDx = 16, kOffYold = 112, kOffUold = 116;
@@ -49,14 +49,16 @@ struct Shape {
   static constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN;
   static constexpr int NO = 4 - NU, NV = 2 * NU, NVO = 2 * NO;
   static constexpr int NOBS = N + kNDist, NTOT = N + kNAug;
-  static constexpr int NACC = NV * (NV + NVO + 1);  // H | Gx | f
-  static constexpr int TPC = 64;                    // threads per controller group
+  static constexpr int NH = NV * (NV + 1) / 2;     // upper triangle of H
+  static constexpr int NACC = NH + NV * NVO + NV;  // H | Gx | f
+  static constexpr int NCH = NY * kNC;             // scan channels
+  static constexpr int TPC = 64;                   // threads per controller group
 };
 
 struct CtrlParams {
   int out_idx[4];     // ControlledOutputIndices
   int ctrl_idx[4];    // ControlInputIndices (local -> system control input)
-  double Q[16];       // ywt, NY x NY row-major
+  double Q[16];       // ywt, NY x NY row-major (symmetric)
   double R[16];       // uwt sub-matrix, NU x NU row-major
   double lower[4], upper[4], rate_lower[4], rate_upper[4];
   double M[15 * 4];   // observer gain, NOBS x 4 row-major
@@ -79,8 +81,8 @@ struct DeviceState {
   double* qpH;         // [B][NCTRL][NV*NV]
   double* qpf;         // [B][NCTRL][NV]
   double* qpG;         // [B][NCTRL][NV*NVO]
-  double* lin;         // [B][NCTRL][N*N + N*kNC]  (Ad | [Bd fd])
-  double* etab;        // [B][NCTRL][p*NY*kNC] (optional, may be null)
+  double* lin;         // [B][NCTRL][N*N + N*kNC]  (Ad | [Bd fd])   (capture only)
+  double* etab;        // [B][NCTRL][p*NY*kNC]                       (capture only)
   int* status;         // [B][NCTRL]
   unsigned* active;    // [B][NCTRL]
   double* objective;   // [B][NCTRL]
@@ -90,12 +92,14 @@ __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
 
-// Shared-memory footprint of one controller group, in doubles.
+// Shared-memory footprint of one controller group, in doubles.  The big region is used three
+// times: RK4 scratch -> powers Ad^(2^j) + L + R -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
   static constexpr int NN = S::N * S::N;
-  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, Ad, BF, scratch, L, R, E, CE, W, red, qp, total;
-  __host__ __device__ SmemLayout(int p, int b_max) {
+  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, Ad, BF, carry, qp, region, L, R, E, total;
+  bool e_alias;
+  __host__ __device__ SmemLayout(int p, int b_max, int n_pow) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     xh = take(S::N);
@@ -109,19 +113,25 @@ struct SmemLayout {
     Cc = take(4 * S::N);
     Ad = take(NN);
     BF = take(S::N * kNC);
-    scratch = take(kMaxPow * NN);            // RK4 scratch, then powers Ad^(2^j)
-    L = take(kBaby * S::NY * S::N);
-    R = take(b_max * S::N * kNC);
-    E = take(kBaby * b_max * S::NY * kNC);
-    CE = take((kBaby * b_max + 1) * S::NY * kNC);
-    W = take(p * S::NY);
-    red = take(2 * S::NACC);
-    qp = take(S::NV * S::NV + S::NV + S::NV * S::NVO + 2 * S::NV + 8);
-    total = o;
+    carry = take((S::TPC / 32) * S::NCH);
+    qp = take(S::NV * S::NV + S::NV + S::NV * (S::NVO > 0 ? S::NVO : 1) + QpFastLayout<S::NV>::size);
+    region = o;
+    const int n_scr = (n_pow > 5 ? n_pow : 5) * NN;
+    L = region + n_scr;
+    R = L + kBaby * S::NY * S::N;
+    const int lr_end = R + b_max * S::N * kNC;
+    const int e_size = kBaby * b_max * S::NCH;
+    const int red_size = S::TPC * (S::NACC | 1);
+    // E can overwrite its own inputs when every thread can hold its tiles in registers
+    e_alias = (kBaby * b_max + S::TPC - 1) / S::TPC <= 2;
+    E = e_alias ? region : lr_end;
+    int end = e_alias ? (lr_end > region + e_size ? lr_end : region + e_size) : lr_end + e_size;
+    if (end < E + red_size) end = E + red_size;
+    total = (end + 1) & ~1;
   }
 };
 
-// C = X * Y for N x N row-major matrices in shared memory, outputs strided over the group.
+// Z = X * Y for N x N row-major matrices in shared memory, outputs strided over the group.
 template <int N>
 __device__ __forceinline__ void matmul_nn(const double* X, const double* Y, double* Z, int t, int nt) {
   for (int idx = t; idx < N * N; idx += nt) {
@@ -133,18 +143,37 @@ __device__ __forceinline__ void matmul_nn(const double* X, const double* Y, doub
   }
 }
 
-// One control step for the scenario owned by this CTA.  y4: the new measurement (global or
-// shared pointer, 4 doubles).  u_out: 4 doubles.  All threads of the CTA must call it.
+// C[r] . dx[0..N) for plant output row r at state x (the non-zeros of C, compressor.cc:169-170).
+template <int PLANT>
+__device__ __forceinline__ double plant_c_row_dot(const double* x, int r, const double* v) {
+  if (PLANT == 0) {
+    if (r < 2) {
+      const double* xc = x + 5 * r;
+      const double* vc = v + 5 * r;
+      return 100 * xc[1] / (kSDc0 * xc[0] * xc[0]) * vc[0] - 100. / (kSDc0 * xc[0]) * vc[1] + 100 * vc[2];
+    }
+    return r == 2 ? v[1] - v[6] : v[10];
+  } else {
+    const int c = r >> 1;
+    const double* xc = x + 5 * c;
+    const double* vc = v + 5 * c;
+    if ((r & 1) == 0) return vc[1];
+    return 100 * xc[1] / (kSDc0 * xc[0] * xc[0]) * vc[0] - 100. / (kSDc0 * xc[0]) * vc[1] + 100 * vc[2];
+  }
+}
+
+// One control step for the scenario owned by this CTA.  y4: the new measurement (4 doubles).
+// u_out: 4 doubles.  All threads of the CTA must call it.
 template <class S>
 __device__ void control_step(const StepParams& P, const DeviceState& G, int scen, const double* y4,
                              double* u_out, double* smem) {
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
-  constexpr int NN = N * N, TPC = S::TPC, NTOT = S::NTOT, NOBS = S::NOBS;
+  constexpr int NN = N * N, TPC = S::TPC, NTOT = S::NTOT, NOBS = S::NOBS, NCH = S::NCH, NH = S::NH;
   const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
   const int p = P.p, b_max = P.b_max;
-  const SmemLayout<S> lay(p, b_max);
+  const SmemLayout<S> lay(p, b_max, P.n_pow);
   double* sm = smem + g * lay.total;
-  double* zbuf = smem + S::NCTRL * lay.total;  // [2][NCTRL][NV] Jacobi exchange + first moves
+  double* zbuf = smem + S::NCTRL * lay.total;  // [NCTRL][NV] plans exchanged between sub-controllers
   const CtrlParams& cp = P.c[g];
   double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   double* ss = G.scen + size_t(scen) * kScenStateStride;
@@ -152,9 +181,9 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   double* xh = sm + lay.xh; double* dx = sm + lay.dx; double* yv = sm + lay.yv;
   double* yold = sm + lay.yold; double* uold = sm + lay.uold; double* ufull = sm + lay.ufull;
   double* ev = sm + lay.ev; double* q = sm + lay.q; double* Cc = sm + lay.Cc;
-  double* Ad = sm + lay.Ad; double* BF = sm + lay.BF; double* scr = sm + lay.scratch;
-  double* L = sm + lay.L; double* R = sm + lay.R; double* E = sm + lay.E; double* CE = sm + lay.CE;
-  double* W = sm + lay.W; double* red = sm + lay.red; double* qpm = sm + lay.qp;
+  double* Ad = sm + lay.Ad; double* BF = sm + lay.BF; double* scr = sm + lay.region;
+  double* L = sm + lay.L; double* R = sm + lay.R; double* E = sm + lay.E;
+  double* carry = sm + lay.carry; double* qpm = sm + lay.qp;
 
   // ---- phase 0: load state -------------------------------------------------------------
   for (int i = t; i < NTOT; i += TPC) dx[i] = gs[kOffDx + i];
@@ -164,46 +193,51 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     uold[t] = gs[kOffUold + t];
     yv[t] = y4[t];
   }
-  if (t < S::NIN) ufull[t] = G.u_offset[size_t(scen) * S::NIN + t];
-  group_sync(g, TPC);
-  // u_full_old = GetPlantInput(u_old_, u_offset_)  (nerve_center.h:140)
-  if (t < 4) {
-    const int plant_idx = (t == 0) ? 0 : (t == 1) ? 3 : (t == 2) ? 4 : 7;
-    ufull[plant_idx] += ss[t];
+  if (t >= 32 && t < 32 + S::NIN) {
+    // u_full_old = GetPlantInput(u_old_, u_offset_)  (nerve_center.h:140)
+    const int i = t - 32;
+    double v = G.u_offset[size_t(scen) * S::NIN + i];
+    if (i == 0) v += ss[0];
+    if (i == 3) v += ss[1];
+    if (i == 4) v += ss[2];
+    if (i == 7) v += ss[3];
+    ufull[i] = v;
   }
+  group_sync(g, TPC);
+
+  // ---- phase 1: Observer::ObserveAPosteriori (observer.cc:24-40), with the C of the
+  //      previous linearisation (same x_hat) ------------------------------------------------
   // delay-line contents relative to u_old (AdjustAllDelayedStates, aug_lin_sys.h:141-154)
   for (int i = t; i < 2 * kDelay; i += TPC) {
     const int d = i / kDelay, tt = i % kDelay;
     const int slot = (tt == 0) ? (NOBS + d) : (NOBS + 2 + d * (kDelay - 1) + tt - 1);
     q[i] = dx[slot] - uold[1 + 2 * d];
   }
-  if (t == 0) plant_c_entry<S::PLANT>(xh, Cc);  // C of the previous linearisation (same x_hat)
+  if (t < 4) ev[t] = yv[t] - yold[t] - (plant_c_row_dot<S::PLANT>(xh, t, dx) + dx[N + t]);
   group_sync(g, TPC);
-
-  // ---- phase 1: Observer::ObserveAPosteriori (observer.cc:24-40) -------------------------
-  if (t < 4) {
-    double cy = dx[N + t];
-    for (int k = 0; k < N; ++k) cy += Cc[t * N + k] * dx[k];
-    ev[t] = yv[t] - yold[t] - cy;
-  }
-  group_sync(g, TPC);
+  double xh_new = 0.0;
   if (t < NOBS) {
-    double acc = 0.0;
+    double acc = dx[t];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc += cp.M[t * 4 + r] * ev[r];
-    dx[t] += acc;
-    if (t < N) xh[t] += dx[t];  // x_ += ObserveAPosteriori(y)  (distributed_controller.cc:80)
+    for (int r = 0; r < 4; ++r) acc = fma(cp.M[t * 4 + r], ev[r], acc);
+    if (t < N) xh_new = xh[t] + acc;  // x_ += ObserveAPosteriori(y)  (distributed_controller.cc:80)
+    dx[t] = acc;
   }
-  group_sync(g, TPC);
-
-  // ---- phase 2: linearise at (x_hat, u_full_old)  (aug_lin_sys.cc:147) --------------------
+  group_sync(g, TPC);  // everyone has read the old xh/dx
+  if (t < N) xh[t] = xh_new;
+  // zero the continuous-time matrices before the sparse fill
   double* Ac = scr;            // continuous A
   double* A2 = scr + NN;
   double* A3 = scr + 2 * NN;
   double* Acom = scr + 3 * NN;
   double* Bc = scr + 4 * NN;   // N x 4
   double* fc = Bc + 4 * N;     // N
-  if (t == 0) plant_linearize<S::PLANT>(xh, ufull, Ac, Bc, Cc, fc);
+  for (int i = t; i < NN; i += TPC) Ac[i] = 0.0;
+  for (int i = t; i < 4 * N; i += TPC) { Bc[i] = 0.0; Cc[i] = 0.0; }
+  group_sync(g, TPC);
+
+  // ---- phase 2: linearise at (x_hat, u_full_old)  (aug_lin_sys.cc:147); three threads ------
+  if (t < 3) plant_linearize_part<S::PLANT>(t, xh, ufull, Ac, Bc, Cc, fc);
   group_sync(g, TPC);
 
   // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) ------------------------------------
@@ -298,99 +332,178 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
 
   // ---- phase 5: E[a + 8b] = L_a R_b --------------------------------------------------------
   const int K = kBaby * b_max;
-  for (int tile = t; tile < K; tile += TPC) {
-    const int a = tile % kBaby, b = tile / kBaby;
-    double acc[NY][kNC];
+  if (lay.e_alias) {
+    // every thread keeps its (at most two) tiles in registers, then E overwrites L, R and the powers
+    double acc[2][NY][kNC];
 #pragma unroll
-    for (int y = 0; y < NY; ++y)
+    for (int ti = 0; ti < 2; ++ti) {
+      const int tile = t + ti * TPC;
 #pragma unroll
-      for (int c = 0; c < kNC; ++c) acc[y][c] = 0.0;
-    const double* Lr = L + a * NY * N;
-    const double* Rb = R + b * N * kNC;
+      for (int y = 0; y < NY; ++y)
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double rv[kNC];
+        for (int c = 0; c < kNC; ++c) acc[ti][y][c] = 0.0;
+      if (tile < K) {
+        const double* Lr = L + (tile % kBaby) * NY * N;
+        const double* Rb = R + (tile / kBaby) * N * kNC;
 #pragma unroll
-      for (int c = 0; c < kNC; ++c) rv[c] = Rb[k * kNC + c];
+        for (int k = 0; k < N; ++k) {
+          double rv[kNC];
 #pragma unroll
-      for (int y = 0; y < NY; ++y) {
-        const double lv = Lr[y * N + k];
+          for (int c = 0; c < kNC; ++c) rv[c] = Rb[k * kNC + c];
 #pragma unroll
-        for (int c = 0; c < kNC; ++c) acc[y][c] = fma(lv, rv[c], acc[y][c]);
-      }
-    }
-    double* Ek = E + tile * NY * kNC;
+          for (int y = 0; y < NY; ++y) {
+            const double lv = Lr[y * N + k];
 #pragma unroll
-    for (int y = 0; y < NY; ++y)
-#pragma unroll
-      for (int c = 0; c < kNC; ++c) Ek[y * kNC + c] = acc[y][c];
-  }
-  group_sync(g, TPC);
-  if (G.etab) {
-    double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NY * kNC);
-    for (int idx = t; idx < p * NY * kNC; idx += TPC) ge[idx] = E[idx];
-  }
-
-  // ---- phase 6: exclusive prefix sums over k, delay-line convolution, w -------------------
-  if (t < NY * kNC) {
-    double run = 0.0;
-    for (int k = 0; k < K; ++k) {
-      CE[k * NY * kNC + t] = run;
-      run += E[k * NY * kNC + t];
-    }
-    CE[K * NY * kNC + t] = run;
-  }
-  group_sync(g, TPC);
-  for (int r = t; r < p; r += TPC) {
-    double conv[NY];
-#pragma unroll
-    for (int y = 0; y < NY; ++y) conv[y] = 0.0;
-    const int tmax = r < kDelay - 1 ? r : kDelay - 1;
-    for (int tt = 0; tt <= tmax; ++tt) {
-      const double q0 = q[tt], q1 = q[kDelay + tt];
-      const double* Er = E + (r - tt) * NY * kNC;
-#pragma unroll
-      for (int y = 0; y < NY; ++y) conv[y] = fma(Er[y * kNC + 1], q0, fma(Er[y * kNC + 3], q1, conv[y]));
-    }
-#pragma unroll
-    for (int y = 0; y < NY; ++y) {
-      const int oy = cp.out_idx[y];
-      const double yref = P.yref[(size_t(g) * p + r) * NY + y];
-      // Sf fd + Sx x_aug - (y_ref - y)   (mpc_qp_solver.cc:31-37)
-      W[r * NY + y] = CE[(r + 1) * NY * kNC + y * kNC + 4] + dx[N + oy] + conv[y] - (yref - yv[oy]);
-    }
-  }
-  group_sync(g, TPC);
-
-  // ---- phase 7: H = Su' Q Su + R, Gx = Su' Q Su_other, f = Su' Q w -----------------------
-  {
-    double acc[S::NACC];
-#pragma unroll
-    for (int i = 0; i < S::NACC; ++i) acc[i] = 0.0;
-    for (int r = t; r < p; r += TPC) {
-      double su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
-      const double* Er = E + r * NY * kNC;
-      const double* Cr = CE + r * NY * kNC;
-      const bool del = r >= kDelay;
-      const double* Ed = E + (del ? r - kDelay : 0) * NY * kNC;
-      const double* Cd = CE + (del ? r - kDelay : 0) * NY * kNC;
-#pragma unroll
-      for (int y = 0; y < NY; ++y) {
-        wv[y] = W[r * NY + y];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool delayed = (i & 1);
-          const double gval = delayed ? (del ? Ed[y * kNC + i] : 0.0) : Er[y * kNC + i];
-          const double pval = delayed ? (del ? Cd[y * kNC + i] : 0.0) : Cr[y * kNC + i];
-          if (i < NU) {
-            su[y][i] = gval;
-            su[y][NU + i] = pval;
-          } else if (NVO > 0) {
-            so[y][i - NU] = gval;
-            so[y][NO + i - NU] = pval;
+            for (int c = 0; c < kNC; ++c) acc[ti][y][c] = fma(lv, rv[c], acc[ti][y][c]);
           }
         }
       }
+    }
+    group_sync(g, TPC);
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti) {
+      const int tile = t + ti * TPC;
+      if (tile < K) {
+#pragma unroll
+        for (int y = 0; y < NY; ++y)
+#pragma unroll
+          for (int c = 0; c < kNC; ++c) E[tile * NCH + y * kNC + c] = acc[ti][y][c];
+      }
+    }
+  } else {
+    for (int tile = t; tile < K; tile += TPC) {
+      double acc[NY][kNC];
+#pragma unroll
+      for (int y = 0; y < NY; ++y)
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) acc[y][c] = 0.0;
+      const double* Lr = L + (tile % kBaby) * NY * N;
+      const double* Rb = R + (tile / kBaby) * N * kNC;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        double rv[kNC];
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) rv[c] = Rb[k * kNC + c];
+#pragma unroll
+        for (int y = 0; y < NY; ++y) {
+          const double lv = Lr[y * N + k];
+#pragma unroll
+          for (int c = 0; c < kNC; ++c) acc[y][c] = fma(lv, rv[c], acc[y][c]);
+        }
+      }
+#pragma unroll
+      for (int y = 0; y < NY; ++y)
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) E[tile * NCH + y * kNC + c] = acc[y][c];
+    }
+  }
+  group_sync(g, TPC);
+  if (G.etab) {
+    double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NCH);
+    for (int idx = t; idx < p * NCH; idx += TPC) ge[idx] = E[idx];
+  }
+
+  // ---- phase 6: QP assembly.  Thread t owns prediction rows [t*rpt, (t+1)*rpt). ---------------
+  //   G_r[y][c]: c < 4 input columns (delayed ones read 40 rows back), c = 4 the fd column
+  //   prefix sums over r by a register scan: local totals -> warp scan -> carry across warps
+  //   w_r = Sf fd + Sx x_aug - (y_ref - y)   (mpc_qp_solver.cc:31-37)
+  //   H = Su' Q Su + R, Gx = Su' Q Su_other, f = Su' Q w accumulated per thread, then reduced.
+  const int rpt = (p + TPC - 1) / TPC;
+  const int r0 = t * rpt;
+  const int r1 = (r0 + rpt < p) ? r0 + rpt : p;
+  auto load_g = [&](int r, double* gv) {
+    const double* Er = E + r * NCH;
+    const bool del = r >= kDelay;
+    const double* Ed = E + (del ? r - kDelay : 0) * NCH;
+#pragma unroll
+    for (int y = 0; y < NY; ++y) {
+      gv[y * kNC + 0] = Er[y * kNC + 0];
+      gv[y * kNC + 1] = del ? Ed[y * kNC + 1] : 0.0;
+      gv[y * kNC + 2] = Er[y * kNC + 2];
+      gv[y * kNC + 3] = del ? Ed[y * kNC + 3] : 0.0;
+      gv[y * kNC + 4] = Er[y * kNC + 4];
+    }
+  };
+  double off[NCH];
+  {
+    double tot[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tot[c] = 0.0;
+    for (int r = r0; r < r1; ++r) {
+      double gv[NCH];
+      load_g(r, gv);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tot[c] += gv[c];
+    }
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      double v = tot[c];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += up;
+      }
+      off[c] = v - tot[c];                       // exclusive prefix inside the warp
+      if (lane == 31) carry[warp * NCH + c] = v;  // warp total
+    }
+    group_sync(g, TPC);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      for (int w = 0; w < warp; ++w) off[c] += carry[w * NCH + c];
+  }
+  // delay-line convolution for the owned rows, E rows shared between neighbouring rows
+  double conv[kMaxRows][NY];
+#pragma unroll
+  for (int j = 0; j < kMaxRows; ++j)
+#pragma unroll
+    for (int y = 0; y < NY; ++y) conv[j][y] = 0.0;
+  if (r0 < p) {
+    const int k_hi = r1 - 1;
+    const int k_lo = (r0 - (kDelay - 1) > 0) ? r0 - (kDelay - 1) : 0;
+    for (int k = k_hi; k >= k_lo; --k) {
+      double e1[NY], e3[NY];
+      const double* Ek = E + k * NCH;
+#pragma unroll
+      for (int y = 0; y < NY; ++y) { e1[y] = Ek[y * kNC + 1]; e3[y] = Ek[y * kNC + 3]; }
+#pragma unroll
+      for (int j = 0; j < kMaxRows; ++j) {
+        const int tt = r0 + j - k;
+        if (j < rpt && tt >= 0 && tt < kDelay && r0 + j < p) {
+          const double q0 = q[tt], q1 = q[kDelay + tt];
+#pragma unroll
+          for (int y = 0; y < NY; ++y) conv[j][y] = fma(e1[y], q0, fma(e3[y], q1, conv[j][y]));
+        }
+      }
+    }
+  }
+  double acc[S::NACC];
+#pragma unroll
+  for (int i = 0; i < S::NACC; ++i) acc[i] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kMaxRows; ++j) {
+    const int r = r0 + j;
+    if (j < rpt && r < p) {
+      double gv[NCH], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
+      load_g(r, gv);
+#pragma unroll
+      for (int y = 0; y < NY; ++y) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < NU) {
+            su[y][i] = gv[y * kNC + i];
+            su[y][NU + i] = off[y * kNC + i];
+          } else if (NVO > 0) {
+            so[y][i - NU] = gv[y * kNC + i];
+            so[y][NO + i - NU] = off[y * kNC + i];
+          }
+        }
+        const int oy = cp.out_idx[y];
+        const double yref = P.yref[(size_t(g) * p + r) * NY + y];
+        wv[y] = (off[y * kNC + 4] + gv[y * kNC + 4]) + dx[N + oy] + conv[j][y] - (yref - yv[oy]);
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) off[c] += gv[c];
 #pragma unroll
       for (int y = 0; y < NY; ++y)
 #pragma unroll
@@ -400,49 +513,61 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
           for (int y2 = 0; y2 < NY; ++y2) s = fma(cp.Q[y * NY + y2], su[y2][v], s);
           qs[y][v] = s;
         }
+      int hi = 0;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
 #pragma unroll
-        for (int v2 = 0; v2 < NV; ++v2)
+        for (int v2 = v; v2 < NV; ++v2, ++hi)
 #pragma unroll
-          for (int y = 0; y < NY; ++y) acc[v * NV + v2] = fma(su[y][v], qs[y][v2], acc[v * NV + v2]);
+          for (int y = 0; y < NY; ++y) acc[hi] = fma(su[y][v], qs[y][v2], acc[hi]);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
 #pragma unroll
         for (int vo = 0; vo < NVO; ++vo)
 #pragma unroll
           for (int y = 0; y < NY; ++y)
-            acc[NV * NV + v * NVO + vo] = fma(so[y][vo], qs[y][v], acc[NV * NV + v * NVO + vo]);
+            acc[NH + v * NVO + vo] = fma(so[y][vo], qs[y][v], acc[NH + v * NVO + vo]);
 #pragma unroll
-        for (int y = 0; y < NY; ++y)
-          acc[NV * NV + NV * NVO + v] = fma(wv[y], qs[y][v], acc[NV * NV + NV * NVO + v]);
+        for (int y = 0; y < NY; ++y) acc[NH + NV * NVO + v] = fma(wv[y], qs[y][v], acc[NH + NV * NVO + v]);
       }
     }
-    // reduce over the group: butterfly inside each warp, then across the two warps
-#pragma unroll
-    for (int i = 0; i < S::NACC; ++i) {
-      double v = acc[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((t & 31) == 0) red[(t >> 5) * S::NACC + i] = v;
-    }
   }
-  group_sync(g, TPC);
-  // qpm: H (NV*NV) | f (NV) | Gx (NV*NVO)
-  for (int i = t; i < S::NACC; i += TPC) {
-    double v = 0.0;
+  group_sync(g, TPC);  // E is dead: reuse it as the reduction buffer
+  {
+    constexpr int RS = S::NACC | 1;  // odd stride: conflict-free 64-bit stores
+    double* red = E;
 #pragma unroll
-    for (int w = 0; w < TPC / 32; ++w) v += red[w * S::NACC + i];
-    if (i < NV * NV) {
-      const int a = i / NV, b = i % NV;
-      if (a / NU == b / NU) v += cp.R[(a % NU) * NU + (b % NU)];  // u_weight_ = I_m (x) uwt
-      qpm[i] = v;
-      G.qpH[(size_t(scen) * S::NCTRL + g) * NV * NV + i] = v;
-    } else if (i < NV * NV + NV * NVO) {
-      qpm[NV * NV + NV + (i - NV * NV)] = v;
-      G.qpG[(size_t(scen) * S::NCTRL + g) * NV * (NVO > 0 ? NVO : 1) + (i - NV * NV)] = v;
-    } else {
-      const int v_i = i - NV * NV - NV * NVO;
-      qpm[NV * NV + v_i] = v;
-      G.qpf[(size_t(scen) * S::NCTRL + g) * NV + v_i] = v;
+    for (int i = 0; i < S::NACC; ++i) red[t * RS + i] = acc[i];
+    group_sync(g, TPC);
+    // qpm: H (NV*NV) | f (NV) | Gx (NV*NVO)
+    if (t < S::NACC) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < TPC; k += 2) {
+        s0 += red[k * RS + t];
+        s1 += red[(k + 1) * RS + t];
+      }
+      const double v = s0 + s1;
+      if (t < NH) {
+        int a = 0, rem = t;
+        while (rem >= NV - a) { rem -= NV - a; ++a; }
+        const int b = a + rem;
+        double hv = v;
+        if (a / NU == b / NU) hv += cp.R[(a % NU) * NU + (b % NU)];  // u_weight_ = I_m (x) uwt
+        qpm[a * NV + b] = hv;
+        qpm[b * NV + a] = hv;
+        double* gH = G.qpH + (size_t(scen) * S::NCTRL + g) * NV * NV;
+        gH[a * NV + b] = hv;
+        gH[b * NV + a] = hv;
+      } else if (t < NH + NV * NVO) {
+        qpm[NV * NV + NV + (t - NH)] = v;
+        G.qpG[(size_t(scen) * S::NCTRL + g) * NV * (NVO > 0 ? NVO : 1) + (t - NH)] = v;
+      } else {
+        const int v_i = t - NH - NV * NVO;
+        qpm[NV * NV + v_i] = v;
+        G.qpf[(size_t(scen) * S::NCTRL + g) * NV + v_i] = v;
+      }
     }
   }
   __syncthreads();
@@ -453,52 +578,64 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     const int c = threadIdx.x;
     const bool on = c < S::NCTRL;
     QpData<NV> qd;
-    double Hm[NV * NV], f0[NV], Gx[NV * (NVO > 0 ? NVO : 1)], z[NV];
-    unsigned guess = kQpNoGuess, act = 0;
+    double f0[NV], z[NV], lam[NV], fi[NV];
+    unsigned wset = kQpNoGuess, act = 0;
     double obj = 0.0;
-    int status = 0;
-    bool pd = true;
+    int status = 0, nq = 0;
+    bool pd = true, fast_ok = false;
+    const double* qm = smem + (on ? c : 0) * lay.total + lay.qp;
+    double* fast = smem + (on ? c : 0) * lay.total + lay.qp + NV * NV + NV + NV * (NVO > 0 ? NVO : 1);
     if (on) {
-      const double* qm = smem + c * lay.total + lay.qp;
       const double* uo = smem + c * lay.total + lay.uold;
       const CtrlParams& cq = P.c[c];
 #pragma unroll
-      for (int i = 0; i < NV * NV; ++i) Hm[i] = qm[i];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) f0[i] = qm[NV * NV + i];
-#pragma unroll
-      for (int i = 0; i < NV * NVO; ++i) Gx[i] = qm[NV * NV + NV + i];
-#pragma unroll
       for (int i = 0; i < NV; ++i) {
+        f0[i] = qm[NV * NV + i];
+        z[i] = 0.0;
         qd.lb[i] = cq.lower[i % NU] - uo[i % NU];
         qd.ub[i] = cq.upper[i % NU] - uo[i % NU];
         qd.lbA[i] = cq.rate_lower[i % NU];
         qd.ubA[i] = cq.rate_upper[i % NU];
       }
-      pd = qp_invert_spd<NV>(Hm, qd.J);
-      guess = G.guess[size_t(scen) * S::NCTRL + c];
+      pd = qp_invert_spd<NV>(qm, qd.J);
+      wset = G.guess[size_t(scen) * S::NCTRL + c];
+      if (pd && wset != kQpNoGuess) fast_ok = qp_prepare<NV, NU>(qd, wset, fast, &nq);
 #pragma unroll
       for (int i = 0; i < NV; ++i) zbuf[c * NV + i] = ss[4 + c * NV + i];  // du_prev = du_old_
     }
     __syncwarp();
     for (int it = 0; it < P.n_iter; ++it) {
       if (on) {
-        double fi[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) fi[i] = f0[i];
         if (NVO > 0) {
           const double* zo = zbuf + (1 - c) * NV;  // the other controller's previous plan
+          const double* Gx = qm + NV * NV + NV;
 #pragma unroll
           for (int i = 0; i < NV; ++i)
 #pragma unroll
             for (int k = 0; k < NVO; ++k) fi[i] = fma(Gx[i * NVO + k], zo[k], fi[i]);
         }
-        if (pd) {
-          status = qp_solve<NV, NU>(qd, Hm, fi, &guess, z, &act, &obj);
-        } else {
+        if (!pd) {
           status = 3;
+        } else if (fast_ok && qp_eval_fast<NV, NU>(qd, fast, nq, wset, fi, z, lam)) {
+          status = 0;
+        } else {
+          // the working set changes (rare): general dual active-set solve, then re-prepare
+          unsigned gset = wset;
+          status = qp_solve<NV, NU>(qd, qm, fi, &gset, z, &act, &obj);
+          if (status == 0) {
+            wset = gset;
+            fast_ok = qp_prepare<NV, NU>(qd, wset, fast, &nq);
+            // multipliers of the new working set for the report below
+            if (fast_ok) qp_eval_fast<NV, NU>(qd, fast, nq, wset, fi, z, lam);
+          } else {
+            fast_ok = false;
+          }
+        }
+        if (status != 0) {
 #pragma unroll
-          for (int i = 0; i < NV; ++i) z[i] = 0.0;
+          for (int i = 0; i < NV; ++i) z[i] = 0.0;   // mpc_qp_solver.cc:66-69
         }
       }
       __syncwarp();
@@ -509,7 +646,31 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
       __syncwarp();
     }
     if (on) {
-      G.guess[size_t(scen) * S::NCTRL + c] = guess;
+      if (status == 0) {
+        // report of the last sweep: active constraints (strictly positive multiplier), objective
+        double fmax = 1.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) fmax = fmax > fabs(fi[i]) ? fmax : fabs(fi[i]);
+        act = 0;
+        int w = 0;
+        for (int j = 0; j < 4 * NV; ++j)
+          if ((wset >> j) & 1u) {
+            if (wset != kQpNoGuess && lam[w] > 1e-9 * fmax) act |= 1u << j;
+            ++w;
+          }
+        obj = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) s = fma(qm[i * NV + k], z[k], s);
+          obj += z[i] * (0.5 * s + fi[i]);
+        }
+        G.guess[size_t(scen) * S::NCTRL + c] = wset;
+      } else {
+        act = 0;
+        obj = 0.0;
+      }
       G.status[size_t(scen) * S::NCTRL + c] = status;
       G.active[size_t(scen) * S::NCTRL + c] = act;
       G.objective[size_t(scen) * S::NCTRL + c] = obj;
@@ -523,9 +684,7 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
 #pragma unroll
     for (int i = 0; i < NU; ++i) du[i] = zbuf[g * NV + i];
     const double h0 = dx[NOBS + 0] - uold[1], h1 = dx[NOBS + 1] - uold[3];
-    double newv[(NTOT + TPC - 1) / TPC];
-    int cnt = 0;
-    for (int i = t; i < NTOT; i += TPC, ++cnt) {
+    for (int i = t; i < NTOT; i += TPC) {
       double v;
       if (i < N) {
         v = BF[i * kNC + 0] * du[0] + BF[i * kNC + 2] * du[2] + BF[i * kNC + 1] * h0 +
@@ -538,11 +697,8 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
         const int cidx = i - NOBS - 2, d = cidx / (kDelay - 1), jj = cidx % (kDelay - 1);
         v = (jj == kDelay - 2) ? uold[1 + 2 * d] + du[1 + 2 * d] : dx[i + 1];
       }
-      newv[cnt] = v;
+      gs[kOffDx + i] = v;
     }
-    group_sync(g, TPC);
-    cnt = 0;
-    for (int i = t; i < NTOT; i += TPC, ++cnt) gs[kOffDx + i] = newv[cnt];
     if (t < N) gs[kOffXhat + t] = xh[t];
     if (t < 4) {
       gs[kOffYold + t] = yv[t];
