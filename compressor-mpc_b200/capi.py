@@ -7,12 +7,13 @@ calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 
 import numpy as np
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libcmpc_b200.so"
+LIB_PATH = pathlib.Path(os.environ.get("CMPC_B200_LIB", _PKG / "libcmpc_b200.so"))
 
 CMPC_OK = 0
 ERR_NAMES = {1: "CMPC_ERR_ARG", 2: "CMPC_ERR_CUDA", 3: "CMPC_ERR_UNSUPPORTED", 4: "CMPC_ERR_STATE"}

@@ -715,8 +715,12 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   if (threadIdx.x < S::NCTRL * NV) ss[4 + threadIdx.x] = zbuf[threadIdx.x];  // du_old_ = du_prev
 }
 
+#ifndef CMPC_MIN_BLOCKS
+#define CMPC_MIN_BLOCKS 3
+#endif
+
 template <class S>
-__global__ void __launch_bounds__(S::NCTRL * S::TPC)
+__global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
 step_kernel(StepParams P, DeviceState G, const double* __restrict__ y, double* __restrict__ u) {
   extern __shared__ __align__(16) double smem[];
   const int scen = blockIdx.x;

@@ -1,4 +1,4 @@
-"""Deterministic synthetic plant scenarios, identical for the GPU path and the oracle.
+"""Deterministic synthetic plant scenarios, identical for the GPU path and its CPU checker.
 
 Scenario 0 is the nominal one of the setup file (so the reference's recorded trajectory
 applies).  For s > 0 a counter-based generator (splitmix64 of seed ^ s) perturbs the

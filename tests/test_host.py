@@ -1,0 +1,133 @@
+"""CPU-only tests: setup-file reader, scenario generator, C-ABI surface, shard/gather logic."""
+import ctypes
+import os
+import re
+import pathlib
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import CASES, ROOT
+
+
+def test_setup_file_roundtrip_and_tokeniser(pkg, setups):
+    sf = pkg.setupfile
+    for case in CASES:
+        s = setups[case]
+        text = sf.format_setup(s)
+        # comments, blank lines and trailing text are tolerated like read_files.h:13-81
+        noisy = "# header comment\n\n" + text.replace("yref\n", "yref\n# reference\n   \n", 1)
+        s2 = sf.parse_setup(noisy, s.plant, s.mode)
+        assert s2.n_iterations == s.n_iterations and s2.output_filename == s.output_filename
+        for k in ("yref", "uwt", "lower", "upper", "rate_lower", "rate_upper", "sim_offsets", "sim_t_end"):
+            assert np.array_equal(getattr(s, k), getattr(s2, k)), k
+        assert all(np.array_equal(a, b) for a, b in zip(s.ywt, s2.ywt))
+    with pytest.raises(RuntimeError):
+        sf.parse_setup("n-iterations\n9\n", 0, 1)              # truncated file
+    with pytest.raises(RuntimeError):
+        sf.parse_setup(text.replace("uwt", "uwx"), s.plant, s.mode)  # wrong key
+
+
+def test_block_end_records_match_reference_driver(setups):
+    # records 0..1000 use block-1 offsets, 10 000 records in total
+    for case in CASES:
+        assert list(setups[case].block_end_records()) == [1001, 10000]
+
+
+def test_scenarios_deterministic_and_shardable(pkg, setups):
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(0)
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, 64, 2000)
+    assert np.array_equal(x0[0], x_def) and list(be[0]) == [1001, 2000] and bo[0, 1, 8] == -0.3
+    assert np.abs(x0[:, [0, 1, 2, 3, 10]] / x_def[[0, 1, 2, 3, 10]] - 1).max() <= 0.01 + 1e-12
+    assert (x0[:, 1] > x0[:, 0]).all() and (x0[:, 4] == 0).all()     # p2 > p1, recycle flow state 0
+    assert (np.abs(be[:, 0] - 1001) <= 200).all() and (be[:, 1] == 2000).all()
+    assert (bo[:, 1, 8] <= -0.15 + 1e-12).all() and (bo[:, 1, 8] >= -0.45 - 1e-12).all()
+    # shards: rank r of 4 gets scenarios [16r, 16r+16)
+    parts = [pkg.scenarios.make_scenarios(s, x_def, 16, 2000, first=16 * r) for r in range(4)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), x0)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), be)
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), bo)
+
+
+def test_c_abi_exports_every_declared_symbol(pkg):
+    """include/cmpc.h vs the built library (no compute calls: there is no GPU here)."""
+    header = (ROOT / "include" / "cmpc.h").read_text()
+    declared = set(re.findall(r"\b(cmpc_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cmpc_handle", "cmpc_config", "cmpc_fp64_peak"}
+    assert len(declared) >= 25
+    lib = pkg.capi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in cmpc.h but not exported"
+    assert declared == set(pkg.capi.EXPORTED_SYMBOLS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(pkg.capi.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (cmpc_[a-z0-9_]+)", nm))
+    assert declared <= exported
+    # host-only entry points work without a GPU
+    cfg = pkg.capi.default_config(0, 1, 4096)
+    assert (cfg.p, cfg.m, cfg.n_controllers, cfg.n_sub_control_inputs, cfg.n_iterations) == (100, 2, 2, 2, 9)
+    assert list(cfg.delays) == [0, 40, 0, 40] and list(cfg.control_input_indices[1]) == [2, 3, 0, 1]
+    x, u = pkg.plant_defaults(1)
+    assert np.array_equal(x, ol.plant_defaults(1)[0]) and np.array_equal(u, ol.plant_defaults(1)[1])
+
+
+def test_product_fails_loudly_without_gpu(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.CmpcError) as e:
+        pkg.NerveCenter(0, 1, batch=4)
+    assert "CMPC_ERR_CUDA" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped path must not import, link or call anything under oracle/."""
+    for path in list((ROOT / "compressor-mpc_b200").rglob("*")) + list((ROOT / "include").rglob("*")):
+        if path.suffix in {".py", ".cu", ".cuh", ".h", ".hpp"} or path.name == "Makefile":
+            text = path.read_text()
+            assert "oracle" not in text.lower(), f"{path} mentions the oracle"
+    so = ROOT / "compressor-mpc_b200" / "libcmpc_b200.so"
+    ldd = subprocess.run(["ldd", str(so)], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+    import json
+    import __graft_entry__ as entry
+    import oracle_lib as ol2
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = entry.load_package()
+    s = pkg.setupfile.setup_from_dict(json.loads((ROOT / "tests/golden/setups.json").read_text())["coop-par"])
+    x_def, _ = ol2.plant_defaults(0)
+    B, T = 3, 25
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T, first=rank * B)
+    tr = ol2.Oracle(s).run_closed_loop(x0, be, bo, T)["traj"]
+    last = torch.from_numpy(np.ascontiguousarray(tr[:, -1, :]))
+    gathered = [torch.empty_like(last) for _ in range(world)]
+    dist.all_gather(gathered, last)                 # the only collective of the N>1 path
+    t_max = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t_max, op=dist.ReduceOp.MAX)    # max-over-ranks timing reduction
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), torch.cat(gathered).numpy())
+        np.save(os.path.join(out_dir, "tmax.npy"), t_max.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_gather_gloo(pkg, setups, tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "gathered.npy")
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(0)
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, 6, 25)
+    ref = ol.Oracle(s).run_closed_loop(x0, be, bo, 25)["traj"][:, -1, :]
+    assert np.array_equal(got, ref)
+    assert np.load(tmp_path / "tmax.npy")[0] == 2.0
