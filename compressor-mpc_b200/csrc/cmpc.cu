@@ -282,6 +282,7 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   int lg = 0;
   while ((1 << lg) < P.b_max) ++lg;
   P.n_pow = 3 + lg;
+  P.ldr = giant_stride(P.b_max);
   P.n_iter = cfg->n_iterations;
   P.batch = cfg->batch;
   P.Ts = cfg->Ts;
@@ -410,8 +411,8 @@ int cmpc_set_capture(cmpc_handle* h, int on) {
   const size_t B = h->cfg.batch, NC = h->NCTRL;
   const size_t ny = h->cfg.n_controlled_outputs[0];
   if (on && !h->G.lin) {
-    CU(dalloc(&h->G.lin, B * NC * (h->N * h->N + h->N * kNC)));
-    CU(dalloc(&h->G.etab, B * NC * size_t(h->cfg.p) * ny * kNC));
+    CU(dalloc(&h->G.lin, B * NC * (h->N * h->N + h->N * 5)));
+    CU(dalloc(&h->G.etab, B * NC * size_t(h->cfg.p) * ny * 5));
   } else if (!on && h->G.lin) {
     CU(cudaDeviceSynchronize());
     cudaFree(h->G.lin); cudaFree(h->G.etab);
@@ -560,7 +561,7 @@ int cmpc_get_linearization(cmpc_handle* h, int ctrl, double* Aorig, double* Bd, 
   if (int rc = check_handle(h)) return rc;
   if (!h->G.lin) return fail(CMPC_ERR_STATE, "enable cmpc_set_capture before the step");
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
-  const int N = h->N, rec = N * N + N * kNC;
+  const int N = h->N, rec = N * N + N * 5;
   const size_t B = h->cfg.batch;
   std::vector<double> buf(B * h->NCTRL * rec);
   CU(cudaDeviceSynchronize());
@@ -569,8 +570,8 @@ int cmpc_get_linearization(cmpc_handle* h, int ctrl, double* Aorig, double* Bd, 
     const double* r = buf.data() + (b * h->NCTRL + ctrl) * rec;
     if (Aorig) std::memcpy(Aorig + b * N * N, r, sizeof(double) * N * N);
     for (int i = 0; i < N; ++i) {
-      if (Bd) for (int c = 0; c < 4; ++c) Bd[(b * N + i) * 4 + c] = r[N * N + i * kNC + c];
-      if (f) f[b * N + i] = r[N * N + i * kNC + 4];
+      if (Bd) for (int c = 0; c < 4; ++c) Bd[(b * N + i) * 4 + c] = r[N * N + i * 5 + c];
+      if (f) f[b * N + i] = r[N * N + i * 5 + 4];
     }
   }
   return CMPC_OK;
@@ -600,7 +601,7 @@ int cmpc_generate_prediction(cmpc_handle* h, int ctrl, double* Su, double* Su_ot
   const size_t B = h->cfg.batch;
   const int p = h->cfg.p, ny = h->cfg.n_controlled_outputs[0], nu = h->cfg.n_sub_control_inputs;
   const int no = 4 - nu, NV = h->NV, NVO = h->NVO;
-  const size_t rec = size_t(p) * ny * kNC;
+  const size_t rec = size_t(p) * ny * 5;
   std::vector<double> E(B * h->NCTRL * rec);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(E.data(), h->G.etab, E.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -612,7 +613,7 @@ int cmpc_generate_prediction(cmpc_handle* h, int ctrl, double* Su, double* Su_ot
         for (int i = 0; i < 4; ++i) {
           const bool delayed = i & 1;
           const int k = delayed ? r - kDelay : r;
-          const double gval = k >= 0 ? e[(size_t(k) * ny + y) * kNC + i] : 0.0;
+          const double gval = k >= 0 ? e[(size_t(k) * ny + y) * 5 + i] : 0.0;
           const size_t row = b * size_t(p) * ny + size_t(r) * ny + y;
           if (i < nu) {
             if (Su) { Su[row * NV + i] = gval; Su[row * NV + nu + i] = run[y * 4 + i]; }

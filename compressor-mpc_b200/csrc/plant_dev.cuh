@@ -262,8 +262,8 @@ __device__ void plant_linearize(const double* x, const double* u, double* A, dou
 // The same linearisation split over three threads (part 0/1: one compressor each, part 2: the
 // coupling terms, the C matrix and the tank).  A, Bc and C must be zeroed by the caller.
 template <int PLANT>
-__device__ void plant_linearize_part(int part, const double* x, const double* u, double* A, double* Bc,
-                                     double* C, double* f) {
+__device__ void plant_linearize_part(int part, const double* x, const double* u, double* A, int lda,
+                                     double* Bc, double* C, double* f) {
   constexpr int N = PlantDims<PLANT>::N;
   if (part < 2) {
     const int i = part, o = 5 * part;
@@ -280,12 +280,12 @@ __device__ void plant_linearize_part(int part, const double* x, const double* u,
       const double m0 = valve_mass_flow<ValveD>(x[1], x[5], u[2], kMoutC);  // first compressor's outflow
       compressor_derivative<false>(x + 5, u + 4, m0, 1.0, f + 5, &m_out);
     }
-    A[(o + 0) * N + o + 0] = j.a00; A[(o + 0) * N + o + 2] = kA02; A[(o + 0) * N + o + 4] = -kA02;
-    A[(o + 1) * N + o + 1] = j.a11; A[(o + 1) * N + o + 2] = kA12; A[(o + 1) * N + o + 4] = -kA12;
-    A[(o + 2) * N + o + 0] = j.a20; A[(o + 2) * N + o + 1] = kA21;
-    A[(o + 2) * N + o + 2] = j.a22; A[(o + 2) * N + o + 3] = j.a23;
-    A[(o + 3) * N + o + 2] = kA32;  A[(o + 3) * N + o + 3] = j.a33;
-    A[(o + 4) * N + o + 0] = -j.a40; A[(o + 4) * N + o + 1] = j.a40; A[(o + 4) * N + o + 4] = kA44;
+    A[(o + 0) * lda + o + 0] = j.a00; A[(o + 0) * lda + o + 2] = kA02; A[(o + 0) * lda + o + 4] = -kA02;
+    A[(o + 1) * lda + o + 1] = j.a11; A[(o + 1) * lda + o + 2] = kA12; A[(o + 1) * lda + o + 4] = -kA12;
+    A[(o + 2) * lda + o + 0] = j.a20; A[(o + 2) * lda + o + 1] = kA21;
+    A[(o + 2) * lda + o + 2] = j.a22; A[(o + 2) * lda + o + 3] = j.a23;
+    A[(o + 3) * lda + o + 2] = kA32;  A[(o + 3) * lda + o + 3] = j.a33;
+    A[(o + 4) * lda + o + 0] = -j.a40; A[(o + 4) * lda + o + 1] = j.a40; A[(o + 4) * lda + o + 4] = kA44;
     Bc[(o + 3) * 4 + 2 * i + 0] = j.b30;
     Bc[(o + 4) * 4 + 2 * i + 1] = j.b41;
     // this compressor's rows of C
@@ -299,22 +299,22 @@ __device__ void plant_linearize_part(int part, const double* x, const double* u,
       // serial coupling: the valve between the compressors (serial_compressors.cc:51-52,70-85);
       // written by this thread after its own block so that A(5,5) is not overwritten
       const double dv1 = valve_derivative<ValveD>(x[1], x[5], u[2], kV1);
-      A[5 * N + 1] = dv1;
-      A[5 * N + 5] = -dv1;
-      A[1 * N + 5] = valve_derivative<ValveD>(x[1], x[5], u[2], kV2);
+      A[5 * lda + 1] = dv1;
+      A[5 * lda + 5] = -dv1;
+      A[1 * lda + 5] = valve_derivative<ValveD>(x[1], x[5], u[2], kV2);
     }
   } else if (PLANT == 0) {
     double a1010 = 0, m_total = 0;
     for (int i = 0; i < 2; ++i) {
       const double p2 = x[5 * i + 1], uo = u[4 * i + 2];
       const double dv_tank = valve_derivative<ValveD>(p2, x[10], uo, kTankVolume);
-      A[10 * N + 5 * i + 1] = dv_tank;
-      A[(5 * i + 1) * N + 10] = valve_derivative<ValveD>(p2, x[10], uo, kV2);
+      A[10 * lda + 5 * i + 1] = dv_tank;
+      A[(5 * i + 1) * lda + 10] = valve_derivative<ValveD>(p2, x[10], uo, kV2);
       a1010 -= dv_tank;
       m_total += valve_mass_flow<ValveD>(p2, x[10], uo, kMoutC);
     }
     a1010 += -valve_derivative<ValveD>(x[10], 1.0, u[8], kTankVolume);
-    A[10 * N + 10] = a1010;
+    A[10 * lda + 10] = a1010;
     C[2 * N + 1] = 1; C[2 * N + 6] = -1;
     C[3 * N + 10] = 1;
     const double m_out_tank = valve_mass_flow<ValveD>(x[10], 1.0, u[8], kMoutC);

@@ -28,6 +28,7 @@
 
 #include "plant_dev.cuh"
 #include "qp_dev.cuh"
+#include "qp_warp.cuh"
 
 namespace cmpc {
 
@@ -35,10 +36,15 @@ constexpr int kDelay = 40;      // Delays = {0,40,0,40} (parallel/serial_compres
 constexpr int kNDist = 4;       // n_disturbance_states
 constexpr int kNAug = kNDist + 2 * kDelay;  // 84
 constexpr int kBaby = 8;        // baby steps a = 0..7
-constexpr int kNC = 5;          // columns of [Bd | fd]
+constexpr int kNC = 6;          // columns of the giant-step blocks: [Bd (4) | fd | X40]
+constexpr int kNS = 5;          // of which need prefix sums over the horizon: [Bd | fd]
+constexpr int kLD = 12;         // row stride of the N x N matrices (N <= 12), conflict-free for DMMA loads
+constexpr int kNNP = kLD * kLD; // storage of one N x N matrix
+constexpr int kLDV = 20;        // row stride of V (N x 16)
 constexpr int kCtrlStateStride = 128;  // doubles per (scenario, controller) in global memory
 constexpr int kScenStateStride = 16;   // doubles per scenario
 constexpr int kMaxRows = 4;     // prediction rows owned by one thread (p <= 4 * TPC)
+constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
 
 // offsets inside one controller's global state record
 constexpr int kOffXhat = 0, kOffDx = 16, kOffYold = 112, kOffUold = 116;
@@ -51,8 +57,10 @@ struct Shape {
   static constexpr int NOBS = N + kNDist, NTOT = N + kNAug;
   static constexpr int NH = NV * (NV + 1) / 2;     // upper triangle of H
   static constexpr int NACC = NH + NV * NVO + NV;  // H | Gx | f
-  static constexpr int NCH = NY * kNC;             // scan channels
+  static constexpr int NCH = NY * kNC;             // doubles per row of the impulse-response table
+  static constexpr int NSC = NY * kNS;             // scan channels
   static constexpr int TPC = 64;                   // threads per controller group
+  static constexpr int WPC = TPC / 32;             // warps per controller group
 };
 
 struct CtrlParams {
@@ -65,7 +73,7 @@ struct CtrlParams {
 };
 
 struct StepParams {
-  int p, b_max, n_pow, n_iter, batch;
+  int p, b_max, n_pow, n_iter, batch, ldr;
   double Ts;
   const double* yref;   // [NCTRL][p][NY]
   CtrlParams c[2];
@@ -81,8 +89,8 @@ struct DeviceState {
   double* qpH;         // [B][NCTRL][NV*NV]
   double* qpf;         // [B][NCTRL][NV]
   double* qpG;         // [B][NCTRL][NV*NVO]
-  double* lin;         // [B][NCTRL][N*N + N*kNC]  (Ad | [Bd fd])   (capture only)
-  double* etab;        // [B][NCTRL][p*NY*kNC]                       (capture only)
+  double* lin;         // [B][NCTRL][N*N + N*5]  (Ad | [Bd fd])   (capture only)
+  double* etab;        // [B][NCTRL][p*NY*5]                       (capture only)
   int* status;         // [B][NCTRL]
   unsigned* active;    // [B][NCTRL]
   double* objective;   // [B][NCTRL]
@@ -92,12 +100,19 @@ __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
 
+// Row stride of the giant-step matrix R (N x b_max*kNC): >= the column count and = 4 or 12
+// mod 16 so that the DMMA B-fragment loads (4 rows x 4 columns per half warp) hit 16 banks.
+__host__ __device__ inline int giant_stride(int b_max) {
+  int ld = b_max * kNC;
+  while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
+  return ld;
+}
+
 // Shared-memory footprint of one controller group, in doubles.  The big region is used three
-// times: RK4 scratch -> powers Ad^(2^j) + L + R -> impulse-response table E -> reduction buffer.
+// times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  static constexpr int NN = S::N * S::N;
-  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, Ad, BF, carry, qp, region, L, R, E, total;
+  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, BF, carry, qp, U, region, L, R, V, lr_end, E, total;
   bool e_alias;
   __host__ __device__ SmemLayout(int p, int b_max, int n_pow) {
     int o = 0;
@@ -111,19 +126,21 @@ struct SmemLayout {
     ev = take(4);
     q = take(2 * kDelay);
     Cc = take(4 * S::N);
-    Ad = take(NN);
     BF = take(S::N * kNC);
-    carry = take((S::TPC / 32) * S::NCH);
+    carry = take(S::WPC * S::NSC);
     qp = take(S::NV * S::NV + S::NV + S::NV * (S::NVO > 0 ? S::NVO : 1) + QpFastLayout<S::NV>::size);
+    U = take(6 * kLD);
     region = o;
-    const int n_scr = (n_pow > 5 ? n_pow : 5) * NN;
+    const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc, Bc|fc; then Ad^(2^j)
     L = region + n_scr;
-    R = L + kBaby * S::NY * S::N;
-    const int lr_end = R + b_max * S::N * kNC;
+    R = L + kBaby * S::NY * kLD;
+    V = R + kLD * giant_stride(b_max);      // 12 rows: rows >= N stay zero (K padding)
+    lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
     const int e_size = kBaby * b_max * S::NCH;
     const int red_size = S::TPC * (S::NACC | 1);
-    // E can overwrite its own inputs when every thread can hold its tiles in registers
-    e_alias = (kBaby * b_max + S::TPC - 1) / S::TPC <= 2;
+    // E can overwrite its own inputs when every warp can hold its output tiles in registers
+    const int n_nt = (b_max * kNC + 7) / 8;
+    e_alias = (n_nt + S::WPC - 1) / S::WPC <= kMaxStageTiles / S::NY;
     E = e_alias ? region : lr_end;
     int end = e_alias ? (lr_end > region + e_size ? lr_end : region + e_size) : lr_end + e_size;
     if (end < E + red_size) end = E + red_size;
@@ -131,15 +148,45 @@ struct SmemLayout {
   }
 };
 
-// Z = X * Y for N x N row-major matrices in shared memory, outputs strided over the group.
-template <int N>
-__device__ __forceinline__ void matmul_nn(const double* X, const double* Y, double* Z, int t, int nt) {
-  for (int idx = t; idx < N * N; idx += nt) {
-    const int i = idx / N, j = idx % N;
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) s = fma(X[i * N + k], Y[k * N + j], s);
-    Z[idx] = s;
+// ---- FP64 tensor-core tiles -----------------------------------------------------------------
+// D(8x8) += A(8x4) * B(4x8), one warp.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)+{0,1}].
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// Operand fragments of one 8-row (A) or 8-column (B) block for K = 12 (three k-tiles).  The
+// operands live zero-padded in shared memory (every matrix slot is cleared at the start of the
+// step and only valid entries are ever written), so the loads need no predicates; rows or
+// columns beyond the matrix only feed output rows/columns that are never stored.
+__device__ __forceinline__ void frag_a(const double* A, int lda, int mt, int lane, double (&a)[3]) {
+  const double* p = A + (8 * mt + (lane >> 2)) * lda + (lane & 3);
+  a[0] = p[0];
+  a[1] = p[4];
+  a[2] = p[8];
+}
+__device__ __forceinline__ void frag_b(const double* B, int ldb, int nt, int lane, double (&b)[3]) {
+  const double* p = B + (lane & 3) * ldb + 8 * nt + (lane >> 2);
+  b[0] = p[0];
+  b[1] = p[4 * ldb];
+  b[2] = p[8 * ldb];
+}
+__device__ __forceinline__ void mma3(double (&c)[2], const double (&a)[3], const double (&b)[3]) {
+  c[0] = 0.0;
+  c[1] = 0.0;
+  dmma_884(c, a[0], b[0]);
+  dmma_884(c, a[1], b[1]);
+  dmma_884(c, a[2], b[2]);
+}
+// Store a tile into a row-major matrix C (stride ldc) at row/column offsets; entries outside
+// [0,mc) x [0,nc) (relative to the tile origin's matrix) are dropped.  Optional + identity.
+__device__ __forceinline__ void tile_store(double* C, int ldc, int row_off, int col_off, int mc, int nc,
+                                           int mt, int nt, int lane, const double (&c)[2], bool add_eye = false) {
+  const int r = 8 * mt + (lane >> 2), cc = 8 * nt + 2 * (lane & 3);
+  if (r < mc) {
+    if (cc < nc) C[(row_off + r) * ldc + col_off + cc] = c[0] + ((add_eye && r == cc) ? 1.0 : 0.0);
+    if (cc + 1 < nc) C[(row_off + r) * ldc + col_off + cc + 1] = c[1] + ((add_eye && r == cc + 1) ? 1.0 : 0.0);
   }
 }
 
@@ -168,9 +215,10 @@ template <class S>
 __device__ void control_step(const StepParams& P, const DeviceState& G, int scen, const double* y4,
                              double* u_out, double* smem) {
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
-  constexpr int NN = N * N, TPC = S::TPC, NTOT = S::NTOT, NOBS = S::NOBS, NCH = S::NCH, NH = S::NH;
+  constexpr int TPC = S::TPC, WPC = S::WPC, NTOT = S::NTOT, NOBS = S::NOBS, NCH = S::NCH, NSC = S::NSC, NH = S::NH;
   const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
-  const int p = P.p, b_max = P.b_max;
+  const int lane = t & 31, warp = t >> 5;
+  const int p = P.p, b_max = P.b_max, ldr = P.ldr;
   const SmemLayout<S> lay(p, b_max, P.n_pow);
   double* sm = smem + g * lay.total;
   double* zbuf = smem + S::NCTRL * lay.total;  // [NCTRL][NV] plans exchanged between sub-controllers
@@ -181,8 +229,8 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   double* xh = sm + lay.xh; double* dx = sm + lay.dx; double* yv = sm + lay.yv;
   double* yold = sm + lay.yold; double* uold = sm + lay.uold; double* ufull = sm + lay.ufull;
   double* ev = sm + lay.ev; double* q = sm + lay.q; double* Cc = sm + lay.Cc;
-  double* Ad = sm + lay.Ad; double* BF = sm + lay.BF; double* scr = sm + lay.region;
-  double* L = sm + lay.L; double* R = sm + lay.R; double* E = sm + lay.E;
+  double* BF = sm + lay.BF; double* scr = sm + lay.region; double* U = sm + lay.U;
+  double* L = sm + lay.L; double* R = sm + lay.R; double* V = sm + lay.V; double* E = sm + lay.E;
   double* carry = sm + lay.carry; double* qpm = sm + lay.qp;
 
   // ---- phase 0: load state -------------------------------------------------------------
@@ -203,6 +251,17 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     if (i == 7) v += ss[3];
     ufull[i] = v;
   }
+  // clear every matrix slot of the region (powers, L, R, V): operands are read zero-padded
+  double* Ac = scr;                 // continuous A (stride kLD)
+  double* A2 = scr + kNNP;
+  double* A3 = scr + 2 * kNNP;
+  double* Acom = scr + 3 * kNNP;
+  double* Xc = scr + 4 * kNNP;      // [Bc (local input order) | fc], N x 5, stride kLD
+  double* Bc = U;                   // N x 4 (system input order), dead before U is used
+  double* fc = U + 4 * N;           // N
+  for (int i = t; i < lay.lr_end - lay.region; i += TPC) scr[i] = 0.0;
+  for (int i = t; i < 6 * kLD; i += TPC) U[i] = 0.0;
+  if (t < 4 * N) Cc[t] = 0.0;
   group_sync(g, TPC);
 
   // ---- phase 1: Observer::ObserveAPosteriori (observer.cc:24-40), with the C of the
@@ -225,182 +284,205 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   }
   group_sync(g, TPC);  // everyone has read the old xh/dx
   if (t < N) xh[t] = xh_new;
-  // zero the continuous-time matrices before the sparse fill
-  double* Ac = scr;            // continuous A
-  double* A2 = scr + NN;
-  double* A3 = scr + 2 * NN;
-  double* Acom = scr + 3 * NN;
-  double* Bc = scr + 4 * NN;   // N x 4
-  double* fc = Bc + 4 * N;     // N
-  for (int i = t; i < NN; i += TPC) Ac[i] = 0.0;
-  for (int i = t; i < 4 * N; i += TPC) { Bc[i] = 0.0; Cc[i] = 0.0; }
   group_sync(g, TPC);
 
   // ---- phase 2: linearise at (x_hat, u_full_old)  (aug_lin_sys.cc:147); three threads ------
-  if (t < 3) plant_linearize_part<S::PLANT>(t, xh, ufull, Ac, Bc, Cc, fc);
+  if (t < 3) plant_linearize_part<S::PLANT>(t, xh, ufull, Ac, kLD, Bc, Cc, fc);
   group_sync(g, TPC);
 
-  // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) ------------------------------------
-  matmul_nn<N>(Ac, Ac, A2, t, TPC);
-  group_sync(g, TPC);
-  matmul_nn<N>(A2, Ac, A3, t, TPC);
-  group_sync(g, TPC);
+  // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) on the FP64 tensor cores -------------
+  // every N x N product is 2 x 2 output tiles of 8 x 8 with K = 12 (3 DMMA per tile); warp w of
+  // the group owns the row block mt = w, so its A fragments are loaded once per product.
+  const int mt_w = warp & 1;
   {
+    double a[3], b0[3], b1[3], c0[2], c1[2];
+    frag_a(Ac, kLD, mt_w, lane, a);
+    frag_b(Ac, kLD, 0, lane, b0);
+    frag_b(Ac, kLD, 1, lane, b1);
+    mma3(c0, a, b0);
+    mma3(c1, a, b1);
+    tile_store(A2, kLD, 0, 0, N, N, mt_w, 0, lane, c0);
+    tile_store(A2, kLD, 0, 0, N, N, mt_w, 1, lane, c1);
+    // [Bd | fd] source with Bd's columns permuted into this controller's input order
+    // (aug_lin_sys.cc:156-173)
+    for (int idx = t; idx < N * 5; idx += TPC) {
+      const int i = idx / 5, cc = idx % 5;
+      Xc[i * kLD + cc] = (cc < 4) ? Bc[i * 4 + cp.ctrl_idx[cc]] : fc[i];
+    }
+    group_sync(g, TPC);
+    frag_a(A2, kLD, mt_w, lane, a);
+    mma3(c0, a, b0);
+    mma3(c1, a, b1);
+    tile_store(A3, kLD, 0, 0, N, N, mt_w, 0, lane, c0);
+    tile_store(A3, kLD, 0, 0, N, N, mt_w, 1, lane, c1);
+    group_sync(g, TPC);
     const double Ts = P.Ts;
-    const double c1 = Ts, c2 = Ts * Ts / 2.0, c3 = Ts * Ts * Ts / 6.0, c4 = Ts * Ts * Ts * Ts / 24.0;
-    for (int idx = t; idx < NN; idx += TPC) {
-      const int i = idx / N, j = idx % N;
-      Acom[idx] = c1 * (i == j ? 1.0 : 0.0) + c2 * Ac[idx] + c3 * A2[idx] + c4 * A3[idx];
+    const double k1 = Ts, k2 = Ts * Ts / 2.0, k3 = Ts * Ts * Ts / 6.0, k4 = Ts * Ts * Ts * Ts / 24.0;
+    for (int idx = t; idx < N * kLD; idx += TPC) {
+      const int i = idx / kLD, j = idx % kLD;
+      if (j < N) Acom[idx] = k1 * (i == j ? 1.0 : 0.0) + k2 * Ac[idx] + k3 * A2[idx] + k4 * A3[idx];
     }
+    group_sync(g, TPC);
+    // Ad = I + Acom Ac (into the A2 slot), [Bd | fd] = Acom Xc
+    double bx[3], cx[2];
+    frag_a(Acom, kLD, mt_w, lane, a);
+    frag_b(Xc, kLD, 0, lane, bx);
+    mma3(c0, a, b0);
+    mma3(c1, a, b1);
+    mma3(cx, a, bx);
+    tile_store(A2, kLD, 0, 0, N, N, mt_w, 0, lane, c0, true);
+    tile_store(A2, kLD, 0, 0, N, N, mt_w, 1, lane, c1, true);
+    tile_store(BF, kNC, 0, 0, N, 5, mt_w, 0, lane, cx);
+    group_sync(g, TPC);
   }
-  group_sync(g, TPC);
-  for (int idx = t; idx < NN + N * kNC; idx += TPC) {
-    if (idx < NN) {
-      const int i = idx / N, j = idx % N;
-      double s = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < N; ++k) s = fma(Acom[i * N + k], Ac[k * N + j], s);
-      Ad[idx] = s;
-    } else {
-      // [Bd | fd] with Bd's columns permuted into this controller's input order
-      // (aug_lin_sys.cc:156-173)
-      const int r = idx - NN, i = r / kNC, c = r % kNC;
-      double s = 0.0;
-      if (c < 4) {
-        const int col = cp.ctrl_idx[c];
-#pragma unroll
-        for (int k = 0; k < N; ++k) s = fma(Acom[i * N + k], Bc[k * 4 + col], s);
-      } else {
-#pragma unroll
-        for (int k = 0; k < N; ++k) s = fma(Acom[i * N + k], fc[k], s);
-      }
-      BF[r] = s;
-    }
-  }
-  group_sync(g, TPC);
+  double* Pw = scr + kNNP;  // Ad lives in the A2 slot: Pw[j] = Ad^(2^j) = scr + (1 + j) kNNP
   if (G.lin) {
-    double* gl = G.lin + (size_t(scen) * S::NCTRL + g) * (NN + N * kNC);
-    for (int idx = t; idx < NN + N * kNC; idx += TPC) gl[idx] = (idx < NN) ? Ad[idx] : BF[idx - NN];
+    double* gl = G.lin + (size_t(scen) * S::NCTRL + g) * (N * N + N * 5);
+    for (int idx = t; idx < N * N + N * 5; idx += TPC)
+      gl[idx] = (idx < N * N) ? Pw[(idx / N) * kLD + idx % N] : BF[((idx - N * N) / 5) * kNC + (idx - N * N) % 5];
   }
 
-  // ---- phase 4: powers Ad^(2^j) with baby (L) and giant (R) steps by doubling -------------
+  // ---- phase 4: powers Ad^(2^j) with baby (L), giant (R) and delay (V) steps by doubling ----
   // L_a = C~ Ad^a (a < 8): rows [2^j, 2^(j+1)) = rows [0, 2^j) * Ad^(2^j), j = 0..2
-  // R_b = Ad^(8b) [Bd fd]: blocks [2^j, 2^(j+1)) = Ad^(8*2^j) * blocks [0, 2^j), j = 0..
-  double* Pw = scr;  // Pw[j] = Ad^(2^j) at scr + j*NN; j = 0 is a copy of Ad
-  for (int idx = t; idx < NN; idx += TPC) Pw[idx] = Ad[idx];
-  for (int idx = t; idx < NY * N; idx += TPC) L[idx] = Cc[cp.out_idx[idx / N] * N + idx % N];
-  for (int idx = t; idx < N * kNC; idx += TPC) R[idx] = BF[idx];
+  // V_a = Ad^a Bd[:, delayed] (a < 8), same doubling on the left
+  // R_b = Ad^(8b) [Bd fd X40]: blocks [2^j, 2^(j+1)) = Ad^(8*2^j) * blocks [0, 2^j), j = 0..
+  // X40 = state reached after the 40 queued delayed inputs have been applied (free response
+  // of the delay line): conv[r] = C~ Ad^(r-39) X40 for r >= 39 comes out of the same table.
+  for (int idx = t; idx < NY * N; idx += TPC) L[(idx / N) * kLD + idx % N] = Cc[cp.out_idx[idx / N] * N + idx % N];
+  for (int idx = t; idx < N * 5; idx += TPC) R[(idx / 5) * ldr + idx % 5] = BF[(idx / 5) * kNC + idx % 5];
+  for (int idx = t; idx < N * 2; idx += TPC) V[(idx >> 1) * kLDV + (idx & 1)] = BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)];
   group_sync(g, TPC);
   for (int s = 1; s <= P.n_pow; ++s) {
-    // (a) Pw[s] = Pw[s-1]^2   (b) L doubling with Pw[s-1], s-1 < 3   (c) R doubling with Pw[s-1], s-1 >= 3
-    const double* Pm = Pw + (s - 1) * NN;
-    const int n_sq = (s < P.n_pow) ? NN : 0;
     const int j = s - 1;
-    int n_l = 0, n_r = 0, r_base = 0;
+    const double* Pm = Pw + j * kNNP;
+    double* Pn = Pw + s * kNNP;
+    if (j == 3) {
+      // X40 = P(P(P(P U_0 + U_1) + U_2) + U_3) + U_4 with U_b = sum_{a,d} V_(7-a)[:, d] q_d[8b + a],
+      // P = Ad^8 = Pm.  Warp 0 of the group, lanes 0..N-1 hold one state each.
+      for (int idx = t; idx < 5 * N; idx += TPC) {
+        const int b = idx / N, i = idx % N;
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < kBaby; ++a) {
+          acc = fma(V[i * kLDV + 2 * (7 - a)], q[8 * b + a], acc);
+          acc = fma(V[i * kLDV + 2 * (7 - a) + 1], q[kDelay + 8 * b + a], acc);
+        }
+        U[b * kLD + i] = acc;
+      }
+      group_sync(g, TPC);
+      if (warp == 0) {
+        double z = (lane < N) ? U[lane] : 0.0;
+        for (int b = 1; b < 5; ++b) {
+          if (lane < kLD) U[5 * kLD + lane] = (lane < N) ? z : 0.0;
+          __syncwarp();
+          if (lane < N) {
+            double a0 = U[b * kLD + lane], a1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; k += 2) {
+              a0 = fma(Pm[lane * kLD + k], U[5 * kLD + k], a0);
+              if (k + 1 < N) a1 = fma(Pm[lane * kLD + k + 1], U[5 * kLD + k + 1], a1);
+            }
+            z = a0 + a1;
+          }
+          __syncwarp();
+        }
+        if (lane < N) R[lane * ldr + 5] = z;
+      }
+      group_sync(g, TPC);
+    }
+    // this warp's row block of Pm multiplies: Pm (squaring), V (j < 3), R (j >= 3);
+    // its column block of Pm is multiplied by the rows of L (j < 3)
+    double a[3], b[3], c[2];
+    frag_a(Pm, kLD, mt_w, lane, a);
+    if (s < P.n_pow) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        frag_b(Pm, kLD, nt, lane, b);
+        mma3(c, a, b);
+        tile_store(Pn, kLD, 0, 0, N, N, mt_w, nt, lane, c);
+      }
+    }
     if (j < 3) {
-      n_l = (1 << j) * NY * N;
+      const int vc = 2 << j, l_rows = (1 << j) * NY;
+      frag_b(V, kLDV, 0, lane, b);
+      mma3(c, a, b);
+      tile_store(V, kLDV, 0, vc, N, vc, mt_w, 0, lane, c);
+      double al[3];
+      frag_b(Pm, kLD, mt_w, lane, b);      // column block nt = w of Pm
+      for (int mt = 0; mt < ((l_rows + 7) >> 3); ++mt) {
+        frag_a(L, kLD, mt, lane, al);
+        mma3(c, al, b);
+        tile_store(L, kLD, l_rows, 0, l_rows, N, mt, mt_w, lane, c);
+      }
     } else {
-      r_base = 1 << (j - 3);
+      const int r_base = 1 << (j - 3);
       int cnt = r_base;
       if (r_base + cnt > b_max) cnt = b_max - r_base;
-      n_r = cnt > 0 ? cnt * N * kNC : 0;
-    }
-    for (int idx = t; idx < n_sq + n_l + n_r; idx += TPC) {
-      if (idx < n_sq) {
-        const int i = idx / N, jj = idx % N;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) acc = fma(Pm[i * N + k], Pm[k * N + jj], acc);
-        Pw[s * NN + idx] = acc;
-      } else if (idx < n_sq + n_l) {
-        const int r = idx - n_sq, row = r / N, col = r % N;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) acc = fma(L[row * N + k], Pm[k * N + col], acc);
-        L[((1 << j) * NY + row) * N + col] = acc;
-      } else {
-        const int r = idx - n_sq - n_l, blk = r / (N * kNC), rr = r % (N * kNC);
-        const int i = rr / kNC, c = rr % kNC;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) acc = fma(Pm[i * N + k], R[(blk * N + k) * kNC + c], acc);
-        R[((r_base + blk) * N + i) * kNC + c] = acc;
+      const int r_cols = cnt > 0 ? cnt * kNC : 0;
+      for (int nt = 0; nt < ((r_cols + 7) >> 3); ++nt) {
+        frag_b(R, ldr, nt, lane, b);
+        mma3(c, a, b);
+        tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt, lane, c);
       }
     }
     group_sync(g, TPC);
   }
 
-  // ---- phase 5: E[a + 8b] = L_a R_b --------------------------------------------------------
-  const int K = kBaby * b_max;
-  if (lay.e_alias) {
-    // every thread keeps its (at most two) tiles in registers, then E overwrites L, R and the powers
-    double acc[2][NY][kNC];
+  // ---- phase 5: E[a + 8b][y][c] = (L_a R_b)[y][c]: (8 NY x N) (N x b_max kNC) on the tensor cores ----
+  // warp w takes the column blocks nt = w, w + WPC, ...; the NY row blocks of L stay in registers.
+  {
+    const int n_nt = (b_max * kNC + 7) >> 3;
+    double al[NY][3];
 #pragma unroll
-    for (int ti = 0; ti < 2; ++ti) {
-      const int tile = t + ti * TPC;
+    for (int mt = 0; mt < NY; ++mt) frag_a(L, kLD, mt, lane, al[mt]);
+    auto store_e = [&](int mt, int nt, const double (&c)[2]) {
+      const int m = 8 * mt + (lane >> 2), n = 8 * nt + 2 * (lane & 3);
+      if (n < b_max * kNC) {
+        const int a = m / NY, y = m % NY, b = n / kNC, cc = n % kNC;
+        double2 v;
+        v.x = c[0];
+        v.y = c[1];
+        *reinterpret_cast<double2*>(E + (a + kBaby * b) * NCH + y * kNC + cc) = v;
+      }
+    };
+    if (lay.e_alias) {
+      constexpr int MAXNT = kMaxStageTiles / NY;   // column blocks per warp held in registers
+      double acc[MAXNT][NY][2];
 #pragma unroll
-      for (int y = 0; y < NY; ++y)
+      for (int i = 0; i < MAXNT; ++i) {
+        const int nt = warp + i * WPC;
+        if (nt < n_nt) {
+          double b[3];
+          frag_b(R, ldr, nt, lane, b);
 #pragma unroll
-        for (int c = 0; c < kNC; ++c) acc[ti][y][c] = 0.0;
-      if (tile < K) {
-        const double* Lr = L + (tile % kBaby) * NY * N;
-        const double* Rb = R + (tile / kBaby) * N * kNC;
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-          double rv[kNC];
-#pragma unroll
-          for (int c = 0; c < kNC; ++c) rv[c] = Rb[k * kNC + c];
-#pragma unroll
-          for (int y = 0; y < NY; ++y) {
-            const double lv = Lr[y * N + k];
-#pragma unroll
-            for (int c = 0; c < kNC; ++c) acc[ti][y][c] = fma(lv, rv[c], acc[ti][y][c]);
-          }
+          for (int mt = 0; mt < NY; ++mt) mma3(acc[i][mt], al[mt], b);
         }
       }
-    }
-    group_sync(g, TPC);
+      group_sync(g, TPC);   // L, R and the powers are dead: E overwrites them
 #pragma unroll
-    for (int ti = 0; ti < 2; ++ti) {
-      const int tile = t + ti * TPC;
-      if (tile < K) {
+      for (int i = 0; i < MAXNT; ++i) {
+        const int nt = warp + i * WPC;
+        if (nt < n_nt) {
 #pragma unroll
-        for (int y = 0; y < NY; ++y)
-#pragma unroll
-          for (int c = 0; c < kNC; ++c) E[tile * NCH + y * kNC + c] = acc[ti][y][c];
-      }
-    }
-  } else {
-    for (int tile = t; tile < K; tile += TPC) {
-      double acc[NY][kNC];
-#pragma unroll
-      for (int y = 0; y < NY; ++y)
-#pragma unroll
-        for (int c = 0; c < kNC; ++c) acc[y][c] = 0.0;
-      const double* Lr = L + (tile % kBaby) * NY * N;
-      const double* Rb = R + (tile / kBaby) * N * kNC;
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        double rv[kNC];
-#pragma unroll
-        for (int c = 0; c < kNC; ++c) rv[c] = Rb[k * kNC + c];
-#pragma unroll
-        for (int y = 0; y < NY; ++y) {
-          const double lv = Lr[y * N + k];
-#pragma unroll
-          for (int c = 0; c < kNC; ++c) acc[y][c] = fma(lv, rv[c], acc[y][c]);
+          for (int mt = 0; mt < NY; ++mt) store_e(mt, nt, acc[i][mt]);
         }
       }
+    } else {
+      for (int nt = warp; nt < n_nt; nt += WPC) {
+        double b[3], c[2];
+        frag_b(R, ldr, nt, lane, b);
 #pragma unroll
-      for (int y = 0; y < NY; ++y)
-#pragma unroll
-        for (int c = 0; c < kNC; ++c) E[tile * NCH + y * kNC + c] = acc[y][c];
+        for (int mt = 0; mt < NY; ++mt) {
+          mma3(c, al[mt], b);
+          store_e(mt, nt, c);
+        }
+      }
     }
   }
   group_sync(g, TPC);
   if (G.etab) {
-    double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NCH);
-    for (int idx = t; idx < p * NCH; idx += TPC) ge[idx] = E[idx];
+    double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NY * 5);
+    for (int idx = t; idx < p * NY * 5; idx += TPC) ge[idx] = E[(idx / 5) * kNC + idx % 5];
   }
 
   // ---- phase 6: QP assembly.  Thread t owns prediction rows [t*rpt, (t+1)*rpt). ---------------
@@ -417,27 +499,26 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     const double* Ed = E + (del ? r - kDelay : 0) * NCH;
 #pragma unroll
     for (int y = 0; y < NY; ++y) {
-      gv[y * kNC + 0] = Er[y * kNC + 0];
-      gv[y * kNC + 1] = del ? Ed[y * kNC + 1] : 0.0;
-      gv[y * kNC + 2] = Er[y * kNC + 2];
-      gv[y * kNC + 3] = del ? Ed[y * kNC + 3] : 0.0;
-      gv[y * kNC + 4] = Er[y * kNC + 4];
+      gv[y * kNS + 0] = Er[y * kNC + 0];
+      gv[y * kNS + 1] = del ? Ed[y * kNC + 1] : 0.0;
+      gv[y * kNS + 2] = Er[y * kNC + 2];
+      gv[y * kNS + 3] = del ? Ed[y * kNC + 3] : 0.0;
+      gv[y * kNS + 4] = Er[y * kNC + 4];
     }
   };
-  double off[NCH];
+  double off[NSC];
   {
-    double tot[NCH];
+    double tot[NSC];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tot[c] = 0.0;
+    for (int c = 0; c < NSC; ++c) tot[c] = 0.0;
     for (int r = r0; r < r1; ++r) {
-      double gv[NCH];
+      double gv[NSC];
       load_g(r, gv);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tot[c] += gv[c];
+      for (int c = 0; c < NSC; ++c) tot[c] += gv[c];
     }
-    const int lane = t & 31, warp = t >> 5;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
+    for (int c = 0; c < NSC; ++c) {
       double v = tot[c];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -445,31 +526,35 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
         if (lane >= o) v += up;
       }
       off[c] = v - tot[c];                       // exclusive prefix inside the warp
-      if (lane == 31) carry[warp * NCH + c] = v;  // warp total
+      if (lane == 31) carry[warp * NSC + c] = v;  // warp total
     }
     group_sync(g, TPC);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
-      for (int w = 0; w < warp; ++w) off[c] += carry[w * NCH + c];
+    for (int c = 0; c < NSC; ++c)
+      for (int w = 0; w < warp; ++w) off[c] += carry[w * NSC + c];
   }
-  // delay-line convolution for the owned rows, E rows shared between neighbouring rows
+  // Sx x_aug, delay-line part: rows r >= 39 read C~ Ad^(r-39) X40 from the table; the first 39
+  // rows see a partially drained delay line and are convolved directly (E rows shared between
+  // neighbouring rows of one thread).
   double conv[kMaxRows][NY];
 #pragma unroll
   for (int j = 0; j < kMaxRows; ++j)
 #pragma unroll
-    for (int y = 0; y < NY; ++y) conv[j][y] = 0.0;
-  if (r0 < p) {
-    const int k_hi = r1 - 1;
-    const int k_lo = (r0 - (kDelay - 1) > 0) ? r0 - (kDelay - 1) : 0;
-    for (int k = k_hi; k >= k_lo; --k) {
+    for (int y = 0; y < NY; ++y) {
+      const int r = r0 + j;
+      conv[j][y] = (j < rpt && r < p && r >= kDelay - 1) ? E[(r - (kDelay - 1)) * NCH + y * kNC + 5] : 0.0;
+    }
+  if (r0 < kDelay - 1 && r0 < p) {
+    const int k_hi = (r1 < kDelay - 1 ? r1 : kDelay - 1) - 1;
+    for (int k = k_hi; k >= 0; --k) {
       double e1[NY], e3[NY];
       const double* Ek = E + k * NCH;
 #pragma unroll
       for (int y = 0; y < NY; ++y) { e1[y] = Ek[y * kNC + 1]; e3[y] = Ek[y * kNC + 3]; }
 #pragma unroll
       for (int j = 0; j < kMaxRows; ++j) {
-        const int tt = r0 + j - k;
-        if (j < rpt && tt >= 0 && tt < kDelay && r0 + j < p) {
+        const int r = r0 + j, tt = r - k;
+        if (j < rpt && tt >= 0 && r < kDelay - 1 && r < p) {
           const double q0 = q[tt], q1 = q[kDelay + tt];
 #pragma unroll
           for (int y = 0; y < NY; ++y) conv[j][y] = fma(e1[y], q0, fma(e3[y], q1, conv[j][y]));
@@ -484,26 +569,26 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   for (int j = 0; j < kMaxRows; ++j) {
     const int r = r0 + j;
     if (j < rpt && r < p) {
-      double gv[NCH], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
+      double gv[NSC], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
       load_g(r, gv);
 #pragma unroll
       for (int y = 0; y < NY; ++y) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < NU) {
-            su[y][i] = gv[y * kNC + i];
-            su[y][NU + i] = off[y * kNC + i];
+            su[y][i] = gv[y * kNS + i];
+            su[y][NU + i] = off[y * kNS + i];
           } else if (NVO > 0) {
-            so[y][i - NU] = gv[y * kNC + i];
-            so[y][NO + i - NU] = off[y * kNC + i];
+            so[y][i - NU] = gv[y * kNS + i];
+            so[y][NO + i - NU] = off[y * kNS + i];
           }
         }
         const int oy = cp.out_idx[y];
         const double yref = P.yref[(size_t(g) * p + r) * NY + y];
-        wv[y] = (off[y * kNC + 4] + gv[y * kNC + 4]) + dx[N + oy] + conv[j][y] - (yref - yv[oy]);
+        wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dx[N + oy] + conv[j][y] - (yref - yv[oy]);
       }
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) off[c] += gv[c];
+      for (int c = 0; c < NSC; ++c) off[c] += gv[c];
 #pragma unroll
       for (int y = 0; y < NY; ++y)
 #pragma unroll
@@ -573,7 +658,109 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   __syncthreads();
 
   // ---- phase 8: n_iter Jacobi sweeps (nerve_center.h:146-158,275-296) ----------------------
-  // lane c of warp 0 owns sub-controller c; plans are exchanged through zbuf.
+  if constexpr (NV == 4 && S::NCTRL == 2) {
+    // warp 0: 16 lanes per sub-controller, everything in registers (qp_warp.cuh)
+    if (threadIdx.x < 32) {
+      const int ln = threadIdx.x;
+      QpLane QL;
+      QL.half = ln >> 4; QL.i = (ln >> 2) & 3; QL.j = ln & 3; QL.base = ln & 16;
+      const int c = QL.half;
+      const double* qm = smem + c * lay.total + lay.qp;
+      const double* uo = smem + c * lay.total + lay.uold;
+      const CtrlParams& cq = P.c[c];
+      const double Hij = qm[QL.i * 4 + QL.j];
+      const double Gij = qm[NV * NV + NV + QL.i * 4 + QL.j];
+      const double f0 = qm[NV * NV + QL.i];
+      // right-hand side of this lane's own constraint (kind = i, variable = j), a'z >= b form
+      double bnd;
+      {
+        const int iu = QL.j & 1;
+        const double lo = cq.lower[iu] - uo[iu], up = cq.upper[iu] - uo[iu];
+        bnd = (QL.i == 0) ? lo : (QL.i == 1) ? -up : (QL.i == 2) ? cq.rate_lower[iu] : -cq.rate_upper[iu];
+      }
+      bool pd;
+      const double J = qw_inverse(Hij, QL, &pd);
+      unsigned wset = G.guess[size_t(scen) * 2 + c];
+      if (wset == kQpNoGuess) wset = 0;          // no warm start: begin from the unconstrained minimiser
+      QpReduced red;
+      bool red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
+      double z_col = ss[4 + c * NV + QL.j];      // du_prev = du_old_ (own plan, entry j)
+      double x_row = 0.0, lam_row = 0.0, f_row = f0;
+      int status = pd ? 0 : 3;
+      for (int it = 0; it < P.n_iter; ++it) {
+        const double zo = __shfl_xor_sync(kFullMask, z_col, 16);   // the other controller's previous plan
+        f_row = f0 + qw_row_sum(Gij * zo);
+        bool ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
+        const bool need_slow = pd && !ok;
+        if (__any_sync(kFullMask, need_slow)) {
+          // the working set changes (rare): lane 0 of the half runs the general dual active-set
+          // solver, the half rebuilds its reduced system for the new set
+          double fi[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) fi[k] = qw_get(f_row, QL, k, 0);
+          unsigned new_w = wset;
+          int st = 0;
+          if (need_slow && ln == QL.base) {
+            QpData<4> qd;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              qd.lb[k] = cq.lower[k & 1] - uo[k & 1];
+              qd.ub[k] = cq.upper[k & 1] - uo[k & 1];
+              qd.lbA[k] = cq.rate_lower[k & 1];
+              qd.ubA[k] = cq.rate_upper[k & 1];
+            }
+            double zs[4], obj_;
+            unsigned act_, gset = kQpNoGuess;
+            st = qp_invert_spd<4>(qm, qd.J) ? qp_solve<4, 2>(qd, qm, fi, &gset, zs, &act_, &obj_) : 3;
+            if (st == 0) new_w = gset;
+          }
+          st = __shfl_sync(kFullMask, st, QL.base);
+          new_w = __shfl_sync(kFullMask, new_w, QL.base);
+          if (need_slow) {
+            status = st;
+            wset = new_w;
+          } else if (pd) {
+            status = 0;
+          }
+          red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
+          ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
+          if (need_slow && st == 0 && !ok) status = 1;   // should not happen: KKT of the new set
+        } else if (pd) {
+          status = 0;
+        }
+        const double xj = qw_get(x_row, QL, QL.j, 0);
+        z_col = (status == 0) ? xj : 0.0;        // mpc_qp_solver.cc:66-69: zeros on failure
+      }
+      if (QL.i == 0) zbuf[c * NV + QL.j] = z_col;
+      // report of the last sweep: active constraints (strictly positive multiplier), objective
+      double fmax = fabs(f_row);
+      fmax = fmax > 1.0 ? fmax : 1.0;
+      {
+        double o = __shfl_xor_sync(kFullMask, fmax, 4);
+        fmax = fmax > o ? fmax : o;
+        o = __shfl_xor_sync(kFullMask, fmax, 8);
+        fmax = fmax > o ? fmax : o;
+      }
+      const int l = ln & 15;
+      const int wpos = __popc(wset & ((1u << l) - 1u));
+      const double lam_l = __shfl_sync(kFullMask, lam_row, QL.base + 4 * (wpos & 3));
+      const bool is_act = ((wset >> l) & 1u) && lam_l > 1e-9 * fmax && status == 0;
+      const unsigned act = (__ballot_sync(kFullMask, is_act) >> QL.base) & 0xffffu;
+      const double zi = x_row;   // z[i] on row i
+      double ob = 0.5 * zi * Hij * z_col + ((QL.j == 0) ? f_row * zi : 0.0);
+      ob += __shfl_xor_sync(kFullMask, ob, 1);
+      ob += __shfl_xor_sync(kFullMask, ob, 2);
+      ob += __shfl_xor_sync(kFullMask, ob, 4);
+      ob += __shfl_xor_sync(kFullMask, ob, 8);
+      if (ln == QL.base) {
+        if (status == 0) G.guess[size_t(scen) * 2 + c] = wset;
+        G.status[size_t(scen) * 2 + c] = status;
+        G.active[size_t(scen) * 2 + c] = status == 0 ? act : 0u;
+        G.objective[size_t(scen) * 2 + c] = status == 0 ? ob : 0.0;
+      }
+    }
+  } else {
+    // lane c of warp 0 owns sub-controller c; plans are exchanged through zbuf.
   if (threadIdx.x < 32) {
     const int c = threadIdx.x;
     const bool on = c < S::NCTRL;
@@ -675,6 +862,7 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
       G.active[size_t(scen) * S::NCTRL + c] = act;
       G.objective[size_t(scen) * S::NCTRL + c] = obj;
     }
+  }
   }
   __syncthreads();
 
