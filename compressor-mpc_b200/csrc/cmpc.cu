@@ -103,8 +103,8 @@ int shape_setup(cmpc_handle* h) {
   h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + S::NCTRL * S::NV + 8);
   if (h->smem_bytes > 227 * 1024)
     return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
-  CU(cudaFuncSetAttribute(step_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          int(h->smem_bytes)));
+  CU(cudaFuncSetAttribute(step_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  CU(cudaFuncSetAttribute(step_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
   return CMPC_OK;
 }
 
@@ -128,7 +128,10 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
     }
     CU(cudaEventRecord(h->ev[h->ev_used], st));
   }
-  step_kernel<S><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
+  if (h->cfg.p <= 2 * S::TPC)
+    step_kernel<S, 2><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
+  else
+    step_kernel<S, 4><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
   h->launches++;
   if (h->timing) {
     CU(cudaEventRecord(h->ev[h->ev_used + 1], st));

@@ -43,7 +43,6 @@ constexpr int kNNP = kLD * kLD; // storage of one N x N matrix
 constexpr int kLDV = 20;        // row stride of V (N x 16)
 constexpr int kCtrlStateStride = 128;  // doubles per (scenario, controller) in global memory
 constexpr int kScenStateStride = 16;   // doubles per scenario
-constexpr int kMaxRows = 4;     // prediction rows owned by one thread (p <= 4 * TPC)
 constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
 
 // offsets inside one controller's global state record
@@ -112,7 +111,7 @@ __host__ __device__ inline int giant_stride(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, BF, carry, qp, U, region, L, R, V, lr_end, E, total;
+  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, BF, carry, qp, U, cz, region, L, R, V, lr_end, E, total;
   bool e_alias;
   __host__ __device__ SmemLayout(int p, int b_max, int n_pow) {
     int o = 0;
@@ -130,6 +129,7 @@ struct SmemLayout {
     carry = take(S::WPC * S::NSC);
     qp = take(S::NV * S::NV + S::NV + S::NV * (S::NVO > 0 ? S::NVO : 1) + QpFastLayout<S::NV>::size);
     U = take(6 * kLD);
+    cz = take(kDelay * S::NY);
     region = o;
     const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc, Bc|fc; then Ad^(2^j)
     L = region + n_scr;
@@ -179,14 +179,17 @@ __device__ __forceinline__ void mma3(double (&c)[2], const double (&a)[3], const
   dmma_884(c, a[1], b[1]);
   dmma_884(c, a[2], b[2]);
 }
-// Store a tile into a row-major matrix C (stride ldc) at row/column offsets; entries outside
-// [0,mc) x [0,nc) (relative to the tile origin's matrix) are dropped.  Optional + identity.
-__device__ __forceinline__ void tile_store(double* C, int ldc, int row_off, int col_off, int mc, int nc,
+// Store a tile into a row-major matrix C (even stride, even column offset) as one 16-byte store
+// per lane.  Rows >= mc and column pairs starting at >= nc_pad are dropped (nc_pad even; a pad
+// column inside the pair receives an exact zero because the B operand's pad column is zero).
+__device__ __forceinline__ void tile_store(double* C, int ldc, int row_off, int col_off, int mc, int nc_pad,
                                            int mt, int nt, int lane, const double (&c)[2], bool add_eye = false) {
   const int r = 8 * mt + (lane >> 2), cc = 8 * nt + 2 * (lane & 3);
-  if (r < mc) {
-    if (cc < nc) C[(row_off + r) * ldc + col_off + cc] = c[0] + ((add_eye && r == cc) ? 1.0 : 0.0);
-    if (cc + 1 < nc) C[(row_off + r) * ldc + col_off + cc + 1] = c[1] + ((add_eye && r == cc + 1) ? 1.0 : 0.0);
+  if (r < mc && cc < nc_pad) {
+    double2 v;
+    v.x = c[0] + ((add_eye && r == cc) ? 1.0 : 0.0);
+    v.y = c[1] + ((add_eye && r == cc + 1) ? 1.0 : 0.0);
+    *reinterpret_cast<double2*>(C + (row_off + r) * ldc + col_off + cc) = v;
   }
 }
 
@@ -211,7 +214,7 @@ __device__ __forceinline__ double plant_c_row_dot(const double* x, int r, const 
 
 // One control step for the scenario owned by this CTA.  y4: the new measurement (4 doubles).
 // u_out: 4 doubles.  All threads of the CTA must call it.
-template <class S>
+template <class S, int RPT>
 __device__ void control_step(const StepParams& P, const DeviceState& G, int scen, const double* y4,
                              double* u_out, double* smem) {
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
@@ -231,7 +234,7 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   double* ev = sm + lay.ev; double* q = sm + lay.q; double* Cc = sm + lay.Cc;
   double* BF = sm + lay.BF; double* scr = sm + lay.region; double* U = sm + lay.U;
   double* L = sm + lay.L; double* R = sm + lay.R; double* V = sm + lay.V; double* E = sm + lay.E;
-  double* carry = sm + lay.carry; double* qpm = sm + lay.qp;
+  double* carry = sm + lay.carry; double* qpm = sm + lay.qp; double* CZ = sm + lay.cz;
 
   // ---- phase 0: load state -------------------------------------------------------------
   for (int i = t; i < NTOT; i += TPC) dx[i] = gs[kOffDx + i];
@@ -301,8 +304,8 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     frag_b(Ac, kLD, 1, lane, b1);
     mma3(c0, a, b0);
     mma3(c1, a, b1);
-    tile_store(A2, kLD, 0, 0, N, N, mt_w, 0, lane, c0);
-    tile_store(A2, kLD, 0, 0, N, N, mt_w, 1, lane, c1);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1);
     // [Bd | fd] source with Bd's columns permuted into this controller's input order
     // (aug_lin_sys.cc:156-173)
     for (int idx = t; idx < N * 5; idx += TPC) {
@@ -313,8 +316,8 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     frag_a(A2, kLD, mt_w, lane, a);
     mma3(c0, a, b0);
     mma3(c1, a, b1);
-    tile_store(A3, kLD, 0, 0, N, N, mt_w, 0, lane, c0);
-    tile_store(A3, kLD, 0, 0, N, N, mt_w, 1, lane, c1);
+    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0);
+    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1);
     group_sync(g, TPC);
     const double Ts = P.Ts;
     const double k1 = Ts, k2 = Ts * Ts / 2.0, k3 = Ts * Ts * Ts / 6.0, k4 = Ts * Ts * Ts * Ts / 24.0;
@@ -330,9 +333,9 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     mma3(c0, a, b0);
     mma3(c1, a, b1);
     mma3(cx, a, bx);
-    tile_store(A2, kLD, 0, 0, N, N, mt_w, 0, lane, c0, true);
-    tile_store(A2, kLD, 0, 0, N, N, mt_w, 1, lane, c1, true);
-    tile_store(BF, kNC, 0, 0, N, 5, mt_w, 0, lane, cx);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0, true);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1, true);
+    tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cx);
     group_sync(g, TPC);
   }
   double* Pw = scr + kNNP;  // Ad lives in the A2 slot: Pw[j] = Ad^(2^j) = scr + (1 + j) kNNP
@@ -371,9 +374,15 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
       }
       group_sync(g, TPC);
       if (warp == 0) {
+        // Z_b = state at the start of delay block b (Z_0 = 0) goes to V[:, b]: phase 5 turns it
+        // into C~ Ad^a Z_b for the rows that still see a partially drained delay line
         double z = (lane < N) ? U[lane] : 0.0;
+        if (lane < kLD) V[lane * kLDV] = 0.0;
         for (int b = 1; b < 5; ++b) {
-          if (lane < kLD) U[5 * kLD + lane] = (lane < N) ? z : 0.0;
+          if (lane < kLD) {
+            U[5 * kLD + lane] = (lane < N) ? z : 0.0;
+            V[lane * kLDV + b] = (lane < N) ? z : 0.0;
+          }
           __syncwarp();
           if (lane < N) {
             double a0 = U[b * kLD + lane], a1 = 0.0;
@@ -399,7 +408,7 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
       for (int nt = 0; nt < 2; ++nt) {
         frag_b(Pm, kLD, nt, lane, b);
         mma3(c, a, b);
-        tile_store(Pn, kLD, 0, 0, N, N, mt_w, nt, lane, c);
+        tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, nt, lane, c);
       }
     }
     if (j < 3) {
@@ -412,7 +421,7 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
       for (int mt = 0; mt < ((l_rows + 7) >> 3); ++mt) {
         frag_a(L, kLD, mt, lane, al);
         mma3(c, al, b);
-        tile_store(L, kLD, l_rows, 0, l_rows, N, mt, mt_w, lane, c);
+        tile_store(L, kLD, l_rows, 0, l_rows, kLD, mt, mt_w, lane, c);
       }
     } else {
       const int r_base = 1 << (j - 3);
@@ -445,6 +454,22 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
         *reinterpret_cast<double2*>(E + (a + kBaby * b) * NCH + y * kNC + cc) = v;
       }
     };
+    if (warp == WPC - 1) {
+      // CZ[r][y] = (L_a Z_b)[y] with r + 1 = 8 b + a: the block-state part of Sx x_aug for r < 39
+      double bz[3], cz[2];
+      frag_b(V, kLDV, 0, lane, bz);
+#pragma unroll
+      for (int mt = 0; mt < NY; ++mt) {
+        mma3(cz, al[mt], bz);
+        const int m = 8 * mt + (lane >> 2), n = 2 * (lane & 3);
+        const int a = m / NY, y = m % NY;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = 8 * (n + e) + a - 1;
+          if (n + e < 5 && r >= 0 && r < kDelay - 1) CZ[r * NY + y] = cz[e];
+        }
+      }
+    }
     if (lay.e_alias) {
       constexpr int MAXNT = kMaxStageTiles / NY;   // column blocks per warp held in registers
       double acc[MAXNT][NY][2];
@@ -490,9 +515,9 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
   //   prefix sums over r by a register scan: local totals -> warp scan -> carry across warps
   //   w_r = Sf fd + Sx x_aug - (y_ref - y)   (mpc_qp_solver.cc:31-37)
   //   H = Su' Q Su + R, Gx = Su' Q Su_other, f = Su' Q w accumulated per thread, then reduced.
-  const int rpt = (p + TPC - 1) / TPC;
-  const int r0 = t * rpt;
-  const int r1 = (r0 + rpt < p) ? r0 + rpt : p;
+  // RPT = rows per thread (compile time): 2 covers p <= 128, 4 covers p <= 256
+  const int r0 = t * RPT;
+  const int r1 = (r0 + RPT < p) ? r0 + RPT : p;
   auto load_g = [&](int r, double* gv) {
     const double* Er = E + r * NCH;
     const bool del = r >= kDelay;
@@ -533,31 +558,28 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     for (int c = 0; c < NSC; ++c)
       for (int w = 0; w < warp; ++w) off[c] += carry[w * NSC + c];
   }
-  // Sx x_aug, delay-line part: rows r >= 39 read C~ Ad^(r-39) X40 from the table; the first 39
-  // rows see a partially drained delay line and are convolved directly (E rows shared between
-  // neighbouring rows of one thread).
-  double conv[kMaxRows][NY];
+  // Sx x_aug, delay-line part.  Rows r >= 39 read C~ Ad^(r-39) X40 from the table.  Rows r < 39
+  // see a partially drained delay line: with r + 1 = 8 b + a the state is Ad^a Z_b plus the a
+  // inputs of the current block, i.e. CZ[r] plus a short convolution (fewer than 8 taps).
+  double conv[RPT][NY];
 #pragma unroll
-  for (int j = 0; j < kMaxRows; ++j)
+  for (int j = 0; j < RPT; ++j) {
+    const int r = r0 + j;
 #pragma unroll
-    for (int y = 0; y < NY; ++y) {
-      const int r = r0 + j;
-      conv[j][y] = (j < rpt && r < p && r >= kDelay - 1) ? E[(r - (kDelay - 1)) * NCH + y * kNC + 5] : 0.0;
-    }
-  if (r0 < kDelay - 1 && r0 < p) {
-    const int k_hi = (r1 < kDelay - 1 ? r1 : kDelay - 1) - 1;
-    for (int k = k_hi; k >= 0; --k) {
-      double e1[NY], e3[NY];
-      const double* Ek = E + k * NCH;
+    for (int y = 0; y < NY; ++y) conv[j][y] = 0.0;
+    if (r < p) {
+      if (r >= kDelay - 1) {
 #pragma unroll
-      for (int y = 0; y < NY; ++y) { e1[y] = Ek[y * kNC + 1]; e3[y] = Ek[y * kNC + 3]; }
+        for (int y = 0; y < NY; ++y) conv[j][y] = E[(r - (kDelay - 1)) * NCH + y * kNC + 5];
+      } else {
+        const int bb = (r + 1) >> 3, aa = (r + 1) & 7;
 #pragma unroll
-      for (int j = 0; j < kMaxRows; ++j) {
-        const int r = r0 + j, tt = r - k;
-        if (j < rpt && tt >= 0 && r < kDelay - 1 && r < p) {
-          const double q0 = q[tt], q1 = q[kDelay + tt];
+        for (int y = 0; y < NY; ++y) conv[j][y] = CZ[r * NY + y];
+        for (int i = 0; i < aa; ++i) {
+          const double* Ek = E + (aa - 1 - i) * NCH;
+          const double q0 = q[8 * bb + i], q1 = q[kDelay + 8 * bb + i];
 #pragma unroll
-          for (int y = 0; y < NY; ++y) conv[j][y] = fma(e1[y], q0, fma(e3[y], q1, conv[j][y]));
+          for (int y = 0; y < NY; ++y) conv[j][y] = fma(Ek[y * kNC + 1], q0, fma(Ek[y * kNC + 3], q1, conv[j][y]));
         }
       }
     }
@@ -566,9 +588,9 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
 #pragma unroll
   for (int i = 0; i < S::NACC; ++i) acc[i] = 0.0;
 #pragma unroll
-  for (int j = 0; j < kMaxRows; ++j) {
+  for (int j = 0; j < RPT; ++j) {
     const int r = r0 + j;
-    if (j < rpt && r < p) {
+    if (r < p) {
       double gv[NSC], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
       load_g(r, gv);
 #pragma unroll
@@ -907,13 +929,13 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
 #define CMPC_MIN_BLOCKS 3
 #endif
 
-template <class S>
+template <class S, int RPT>
 __global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
 step_kernel(StepParams P, DeviceState G, const double* __restrict__ y, double* __restrict__ u) {
   extern __shared__ __align__(16) double smem[];
   const int scen = blockIdx.x;
   if (scen >= P.batch) return;
-  control_step<S>(P, G, scen, y + size_t(scen) * 4, u + size_t(scen) * 4, smem);
+  control_step<S, RPT>(P, G, scen, y + size_t(scen) * 4, u + size_t(scen) * 4, smem);
 }
 
 }  // namespace cmpc
