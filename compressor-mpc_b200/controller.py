@@ -152,9 +152,9 @@ class NerveCenter:
         check(lib().cmpc_set_timing(self._h, int(on)))
 
     def get_timing(self):
-        n = C.c_int64(); ms = C.c_double()
-        check(lib().cmpc_get_timing(self._h, C.byref(n), C.byref(ms)))
-        return n.value, ms.value
+        n = C.c_int64(); ms = C.c_double(); ams = C.c_double()
+        check(lib().cmpc_get_timing(self._h, C.byref(n), C.byref(ms), C.byref(ams)))
+        return n.value, ms.value, ams.value
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,11 +101,22 @@ int find_shape(const cmpc_config& c) {
 template <class S>
 int shape_setup(cmpc_handle* h) {
   const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow);
-  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + S::NCTRL * S::NV + 8);
+  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 8);
   if (h->smem_bytes > 227 * 1024)
     return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
-  CU(cudaFuncSetAttribute(step_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
-  CU(cudaFuncSetAttribute(step_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  CU(cudaFuncSetAttribute(assemble_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  CU(cudaFuncSetAttribute(assemble_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  // ask for the largest shared-memory carveout: occupancy of this kernel is bounded by shared memory
+  CU(cudaFuncSetAttribute(assemble_kernel<S, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(assemble_kernel<S, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (getenv("CMPC_DEBUG")) {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, assemble_kernel<S, 2>, S::NCTRL * S::TPC, h->smem_bytes);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, assemble_kernel<S, 2>);
+    fprintf(stderr, "[cmpc] assemble_kernel: smem %zu B/CTA, %d regs, %zu B local, occupancy %d CTAs/SM\n",
+            h->smem_bytes, fa.numRegs, fa.localSizeBytes, nb);
+  }
   return CMPC_OK;
 }
 
@@ -120,23 +132,32 @@ int launch_init(cmpc_handle* h, const double* x, const double* u, const double* 
 
 template <class S>
 int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
+  const int B = h->cfg.batch;
+  cudaEvent_t* ev = nullptr;
   if (h->timing) {
-    if (h->ev_used + 2 > h->ev.size()) {
+    if (h->ev_used + 4 > h->ev.size()) {
       const size_t old = h->ev.size();
-      h->ev.resize(old + 512);
+      h->ev.resize(old + 1024);
       for (size_t i = old; i < h->ev.size(); ++i) CU(cudaEventCreate(&h->ev[i]));
     }
-    CU(cudaEventRecord(h->ev[h->ev_used], st));
+    ev = &h->ev[h->ev_used];
+    h->ev_used += 4;
+    CU(cudaEventRecord(ev[0], st));
   }
+  // K0: observer + linearisation, 4 threads per (scenario, controller)
+  const int n_thr = B * S::NCTRL * 4;
+  lin_kernel<S><<<(n_thr + 127) / 128, 128, 0, st>>>(h->P, h->G, y);
+  if (ev) CU(cudaEventRecord(ev[1], st));
+  // K1: discretisation, prediction, QP assembly; one CTA per scenario
   if (h->cfg.p <= 2 * S::TPC)
-    step_kernel<S, 2><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
+    assemble_kernel<S, 2><<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
   else
-    step_kernel<S, 4><<<h->cfg.batch, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y, u);
-  h->launches++;
-  if (h->timing) {
-    CU(cudaEventRecord(h->ev[h->ev_used + 1], st));
-    h->ev_used += 2;
-  }
+    assemble_kernel<S, 4><<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
+  if (ev) CU(cudaEventRecord(ev[2], st));
+  // K2: Jacobi sweeps + update; one warp per scenario
+  solve_kernel<S><<<(B + 3) / 4, 128, 0, st>>>(h->P, h->G, u);
+  if (ev) CU(cudaEventRecord(ev[3], st));
+  h->launches += 3;
   CU(cudaGetLastError());
   return CMPC_OK;
 }
@@ -309,12 +330,14 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   A(dalloc(&G.guess, size_t(B) * NC));
   A(dalloc(&G.scen, size_t(B) * kScenStateStride));
   A(dalloc(&G.u_offset, size_t(B) * h->NIN));
+  A(dalloc(&G.work, size_t(B) * NC * kWorkStride));
   A(dalloc(&G.qpH, size_t(B) * NC * h->NV * h->NV));
   A(dalloc(&G.qpf, size_t(B) * NC * h->NV));
   A(dalloc(&G.qpG, size_t(B) * NC * h->NV * (h->NVO > 0 ? h->NVO : 1)));
   A(dalloc(&G.status, size_t(B) * NC));
   A(dalloc(&G.active, size_t(B) * NC));
   A(dalloc(&G.objective, size_t(B) * NC));
+  A(dalloc(&G.ticks, size_t(B) * 16));
   A(dalloc(&h->d_yref, size_t(NC) * cfg->p * 4));
   A(dalloc(&h->d_y, size_t(B) * 4));
   A(dalloc(&h->d_u, size_t(B) * 4));
@@ -342,8 +365,8 @@ int cmpc_destroy(cmpc_handle* h) {
   if (!h) return CMPC_OK;
   cudaSetDevice(h->device);
   DeviceState& G = h->G;
-  void* ptrs[] = {G.ctrl, G.guess, G.scen, G.u_offset, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
-                  G.active, G.objective, h->d_yref, h->d_y, h->d_u, h->d_xinit, h->d_uinit,
+  void* ptrs[] = {G.ctrl, G.guess, G.scen, G.u_offset, G.work, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
+                  G.active, G.objective, G.ticks, h->d_yref, h->d_y, h->d_u, h->d_xinit, h->d_uinit,
                   h->d_uinitfull, h->d_yinit, h->d_x, h->d_ring, h->d_block_end, h->d_block_off};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -473,6 +496,13 @@ int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double
   return CMPC_OK;
 }
 
+int cmpc_debug_phase_ticks(cmpc_handle* h, long long* out /* B x 16 */) {
+  if (int rc = check_handle(h)) return rc;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, h->G.ticks, size_t(h->cfg.batch) * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return CMPC_OK;
+}
+
 int cmpc_launch_count(cmpc_handle* h, int64_t* n) {
   if (!h || !n) return fail(CMPC_ERR_ARG, "null argument");
   *n = h->launches;
@@ -506,17 +536,20 @@ int cmpc_set_timing(cmpc_handle* h, int on) {
   return CMPC_OK;
 }
 
-int cmpc_get_timing(cmpc_handle* h, int64_t* n_step_launches, double* step_kernel_ms) {
+int cmpc_get_timing(cmpc_handle* h, int64_t* n_steps, double* step_ms, double* assemble_ms) {
   if (int rc = check_handle(h)) return rc;
   CU(cudaDeviceSynchronize());
-  double total = 0.0;
-  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+  double total = 0.0, asm_ms = 0.0;
+  for (size_t i = 0; i + 3 < h->ev_used; i += 4) {
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    CU(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 3]));
     total += ms;
+    CU(cudaEventElapsedTime(&ms, h->ev[i + 1], h->ev[i + 2]));
+    asm_ms += ms;
   }
-  if (n_step_launches) *n_step_launches = int64_t(h->ev_used / 2);
-  if (step_kernel_ms) *step_kernel_ms = total;
+  if (n_steps) *n_steps = int64_t(h->ev_used / 4);
+  if (step_ms) *step_ms = total;
+  if (assemble_ms) *assemble_ms = asm_ms;
   h->ev_used = 0;
   return CMPC_OK;
 }

@@ -260,25 +260,27 @@ __device__ void plant_linearize(const double* x, const double* u, double* A, dou
 }
 
 // The same linearisation split over three threads (part 0/1: one compressor each, part 2: the
-// coupling terms, the C matrix and the tank).  A, Bc and C must be zeroed by the caller.
+// coupling terms and the tank).  Writes only the entries that can be non-zero: A (stride lda),
+// X = [B (columns permuted by inv: system input -> column) | f] (stride ldx), C (4 x N dense).
+// The destination's other entries must already be zero (they never change).
 template <int PLANT>
-__device__ void plant_linearize_part(int part, const double* x, const double* u, double* A, int lda,
-                                     double* Bc, double* C, double* f) {
+__device__ void plant_linearize_part_x(int part, const double* x, const double* u, double* A, int lda,
+                                       double* X, int ldx, const int* inv, double* C) {
   constexpr int N = PlantDims<PLANT>::N;
   if (part < 2) {
     const int i = part, o = 5 * part;
     CompJac j;
-    double m_out;
+    double m_out, fl[5];
     if (PLANT == 0) {
       compressor_jacobian<true>(x + o, u + 4 * i, 1.0, x[10], &j);
-      compressor_derivative<true>(x + o, u + 4 * i, 1.0, x[10], f + o, &m_out);
+      compressor_derivative<true>(x + o, u + 4 * i, 1.0, x[10], fl, &m_out);
     } else if (i == 0) {
       compressor_jacobian<true>(x, u, 1.0, x[5], &j);
-      compressor_derivative<true>(x, u, 1.0, x[5], f, &m_out);
+      compressor_derivative<true>(x, u, 1.0, x[5], fl, &m_out);
     } else {
       compressor_jacobian<false>(x + 5, u + 4, -1.0, 1.0, &j);
       const double m0 = valve_mass_flow<ValveD>(x[1], x[5], u[2], kMoutC);  // first compressor's outflow
-      compressor_derivative<false>(x + 5, u + 4, m0, 1.0, f + 5, &m_out);
+      compressor_derivative<false>(x + 5, u + 4, m0, 1.0, fl, &m_out);
     }
     A[(o + 0) * lda + o + 0] = j.a00; A[(o + 0) * lda + o + 2] = kA02; A[(o + 0) * lda + o + 4] = -kA02;
     A[(o + 1) * lda + o + 1] = j.a11; A[(o + 1) * lda + o + 2] = kA12; A[(o + 1) * lda + o + 4] = -kA12;
@@ -286,8 +288,10 @@ __device__ void plant_linearize_part(int part, const double* x, const double* u,
     A[(o + 2) * lda + o + 2] = j.a22; A[(o + 2) * lda + o + 3] = j.a23;
     A[(o + 3) * lda + o + 2] = kA32;  A[(o + 3) * lda + o + 3] = j.a33;
     A[(o + 4) * lda + o + 0] = -j.a40; A[(o + 4) * lda + o + 1] = j.a40; A[(o + 4) * lda + o + 4] = kA44;
-    Bc[(o + 3) * 4 + 2 * i + 0] = j.b30;
-    Bc[(o + 4) * 4 + 2 * i + 1] = j.b41;
+    X[(o + 3) * ldx + inv[2 * i + 0]] = j.b30;
+    X[(o + 4) * ldx + inv[2 * i + 1]] = j.b41;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) X[(o + r) * ldx + 4] = fl[r];
     // this compressor's rows of C
     if (PLANT == 0) {
       C[i * N + o + 0] = j.c10; C[i * N + o + 1] = j.c11; C[i * N + o + 2] = 100;
@@ -318,7 +322,7 @@ __device__ void plant_linearize_part(int part, const double* x, const double* u,
     C[2 * N + 1] = 1; C[2 * N + 6] = -1;
     C[3 * N + 10] = 1;
     const double m_out_tank = valve_mass_flow<ValveD>(x[10], 1.0, u[8], kMoutC);
-    f[10] = (340.0 * 340.0) / kTankVolume * (m_total - m_out_tank) * 1e-5;
+    X[10 * ldx + 4] = (340.0 * 340.0) / kTankVolume * (m_total - m_out_tank) * 1e-5;
   }
 }
 

@@ -1,5 +1,11 @@
-// The batched control step: one CTA per plant scenario, one thread group per
-// sub-controller, everything between "new measurement y" and "next input u" on chip.
+// The batched control step as three back-to-back launches on one stream (no host round trip),
+// each shaped after the parallelism its part of the step offers:
+//   lin_kernel       observer a-posteriori + plant linearisation: scalar code, 4 threads per
+//                    (scenario, sub-controller), tens of thousands of threads in flight
+//   assemble_kernel  discretisation, prediction and QP assembly: small dense matrix algebra on the
+//                    FP64 tensor cores, one CTA per scenario, one thread group per sub-controller
+//   solve_kernel     Jacobi sweeps of the QP solves, first move, a-priori observer update: one
+//                    warp per scenario (16 lanes per sub-controller)
 //
 // Reference path replaced: NerveCenter::GetNextInputWithTiming
 // (include/nerve_center.h:134-182) -> DistributedController::GenerateInitialQP
@@ -43,6 +49,9 @@ constexpr int kNNP = kLD * kLD; // storage of one N x N matrix
 constexpr int kLDV = 20;        // row stride of V (N x 16)
 constexpr int kCtrlStateStride = 128;  // doubles per (scenario, controller) in global memory
 constexpr int kScenStateStride = 16;   // doubles per scenario
+// hand-over record of one (scenario, controller): continuous A (12 x 12, zero padded),
+// [Bc | fc] in the controller's input order (12 x 12, zero padded), C (4 x N), [Bd | fd] (N x 6)
+constexpr int kWorkStride = 512, kWAc = 0, kWXc = 144, kWCc = 288, kWBF = 336;
 constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
 
 // offsets inside one controller's global state record
@@ -84,6 +93,7 @@ struct DeviceState {
   unsigned* guess;     // [B][NCTRL]
   double* scen;        // [B][kScenStateStride]: u_old (4, system order), du_old (8)
   double* u_offset;    // [B][NIN]
+  double* work;        // [B][NCTRL][kWorkStride] hand-over between the three kernels
   // results / parity hooks of the last step
   double* qpH;         // [B][NCTRL][NV*NV]
   double* qpf;         // [B][NCTRL][NV]
@@ -93,6 +103,7 @@ struct DeviceState {
   int* status;         // [B][NCTRL]
   unsigned* active;    // [B][NCTRL]
   double* objective;   // [B][NCTRL]
+  long long* ticks;    // [B][16] per-phase clock64() stamps (CMPC_PHASE_TIMING builds only)
 };
 
 __device__ __forceinline__ void group_sync(int g, int nthreads) {
@@ -111,27 +122,21 @@ __host__ __device__ inline int giant_stride(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int xh, dx, yv, yold, uold, ufull, ev, q, Cc, BF, carry, qp, U, cz, region, L, R, V, lr_end, E, total;
+  int yv, dxd, q, Cc, BF, carry, U, cz, region, L, R, V, lr_end, E, total;
   bool e_alias;
   __host__ __device__ SmemLayout(int p, int b_max, int n_pow) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
-    xh = take(S::N);
-    dx = take(S::NTOT);
     yv = take(4);
-    yold = take(4);
-    uold = take(4);
-    ufull = take(S::NIN);
-    ev = take(4);
+    dxd = take(4);
     q = take(2 * kDelay);
     Cc = take(4 * S::N);
     BF = take(S::N * kNC);
     carry = take(S::WPC * S::NSC);
-    qp = take(S::NV * S::NV + S::NV + S::NV * (S::NVO > 0 ? S::NVO : 1) + QpFastLayout<S::NV>::size);
     U = take(6 * kLD);
     cz = take(kDelay * S::NY);
     region = o;
-    const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc, Bc|fc; then Ad^(2^j)
+    const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then Ad^(2^j)
     L = region + n_scr;
     R = L + kBaby * S::NY * kLD;
     V = R + kLD * giant_stride(b_max);      // 12 rows: rows >= N stay zero (K padding)
@@ -214,83 +219,114 @@ __device__ __forceinline__ double plant_c_row_dot(const double* x, int r, const 
 
 // One control step for the scenario owned by this CTA.  y4: the new measurement (4 doubles).
 // u_out: 4 doubles.  All threads of the CTA must call it.
+#ifndef CMPC_MIN_BLOCKS
+#define CMPC_MIN_BLOCKS 3
+#endif
+
+// ---- K0: Observer::ObserveAPosteriori (observer.cc:24-40) with the C of the previous
+// linearisation (same x_hat), x_ += dx (distributed_controller.cc:80), then the plant is
+// linearised at (x_hat, u_full_old) (aug_lin_sys.cc:147).  Four threads per (scenario,
+// controller): each repeats the tiny observer update in registers, three of them fill one part
+// of the continuous-time matrices in the hand-over record (whose zero pattern never changes).
+template <class S>
+__global__ void __launch_bounds__(128)
+lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
+  constexpr int N = S::N, NOBS = S::NOBS, NIN = S::NIN;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int part = tid & 3, quad = tid >> 2;
+  const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
+  if (scen >= P.batch) return;
+  const CtrlParams& cp = P.c[g];
+  double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
+  const double* ss = G.scen + size_t(scen) * kScenStateStride;
+  double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
+  double xh[N], dx[NOBS], ev[4], yv[4];
+#pragma unroll
+  for (int i = 0; i < N; ++i) xh[i] = gs[kOffXhat + i];
+#pragma unroll
+  for (int i = 0; i < NOBS; ++i) dx[i] = gs[kOffDx + i];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    yv[r] = y[size_t(scen) * 4 + r];
+    ev[r] = yv[r] - gs[kOffYold + r] - (plant_c_row_dot<S::PLANT>(xh, r, dx) + dx[N + r]);
+  }
+#pragma unroll
+  for (int i = 0; i < NOBS; ++i) {
+    double acc = dx[i];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc = fma(cp.M[i * 4 + r], ev[r], acc);
+    dx[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) xh[i] += dx[i];
+  if (part == 3) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) gs[kOffXhat + i] = xh[i];
+#pragma unroll
+    for (int i = 0; i < NOBS; ++i) gs[kOffDx + i] = dx[i];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) gs[kOffYold + r] = yv[r];
+    return;
+  }
+  // u_full_old = GetPlantInput(u_old_, u_offset_)  (nerve_center.h:140)
+  double uf[NIN];
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) uf[i] = G.u_offset[size_t(scen) * NIN + i];
+  uf[0] += ss[0]; uf[3] += ss[1]; uf[4] += ss[2]; uf[7] += ss[3];
+  int inv[4];   // system control input -> this controller's local input (aug_lin_sys.cc:156-173)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) inv[cp.ctrl_idx[c]] = c;
+  plant_linearize_part_x<S::PLANT>(part, xh, uf, wk + kWAc, kLD, wk + kWXc, kLD, inv, wk + kWCc);
+}
+
+// ---- K1: discretisation, prediction and QP assembly of one scenario per CTA --------------------
 template <class S, int RPT>
-__device__ void control_step(const StepParams& P, const DeviceState& G, int scen, const double* y4,
-                             double* u_out, double* smem) {
+__global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
+assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
+  extern __shared__ __align__(16) double smem[];
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
-  constexpr int TPC = S::TPC, WPC = S::WPC, NTOT = S::NTOT, NOBS = S::NOBS, NCH = S::NCH, NSC = S::NSC, NH = S::NH;
+  constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NCH = S::NCH, NSC = S::NSC, NH = S::NH;
+  const int scen = blockIdx.x;
+  if (scen >= P.batch) return;
   const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
   const int lane = t & 31, warp = t >> 5;
   const int p = P.p, b_max = P.b_max, ldr = P.ldr;
   const SmemLayout<S> lay(p, b_max, P.n_pow);
   double* sm = smem + g * lay.total;
-  double* zbuf = smem + S::NCTRL * lay.total;  // [NCTRL][NV] plans exchanged between sub-controllers
   const CtrlParams& cp = P.c[g];
-  double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
-  double* ss = G.scen + size_t(scen) * kScenStateStride;
+  const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
+  double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
 
-  double* xh = sm + lay.xh; double* dx = sm + lay.dx; double* yv = sm + lay.yv;
-  double* yold = sm + lay.yold; double* uold = sm + lay.uold; double* ufull = sm + lay.ufull;
-  double* ev = sm + lay.ev; double* q = sm + lay.q; double* Cc = sm + lay.Cc;
+  double* yv = sm + lay.yv; double* dxd = sm + lay.dxd; double* q = sm + lay.q; double* Cc = sm + lay.Cc;
   double* BF = sm + lay.BF; double* scr = sm + lay.region; double* U = sm + lay.U;
   double* L = sm + lay.L; double* R = sm + lay.R; double* V = sm + lay.V; double* E = sm + lay.E;
-  double* carry = sm + lay.carry; double* qpm = sm + lay.qp; double* CZ = sm + lay.cz;
-
-  // ---- phase 0: load state -------------------------------------------------------------
-  for (int i = t; i < NTOT; i += TPC) dx[i] = gs[kOffDx + i];
-  if (t < N) xh[t] = gs[kOffXhat + t];
-  if (t < 4) {
-    yold[t] = gs[kOffYold + t];
-    uold[t] = gs[kOffUold + t];
-    yv[t] = y4[t];
-  }
-  if (t >= 32 && t < 32 + S::NIN) {
-    // u_full_old = GetPlantInput(u_old_, u_offset_)  (nerve_center.h:140)
-    const int i = t - 32;
-    double v = G.u_offset[size_t(scen) * S::NIN + i];
-    if (i == 0) v += ss[0];
-    if (i == 3) v += ss[1];
-    if (i == 4) v += ss[2];
-    if (i == 7) v += ss[3];
-    ufull[i] = v;
-  }
-  // clear every matrix slot of the region (powers, L, R, V): operands are read zero-padded
+  double* carry = sm + lay.carry; double* CZ = sm + lay.cz;
   double* Ac = scr;                 // continuous A (stride kLD)
   double* A2 = scr + kNNP;
   double* A3 = scr + 2 * kNNP;
   double* Acom = scr + 3 * kNNP;
   double* Xc = scr + 4 * kNNP;      // [Bc (local input order) | fc], N x 5, stride kLD
-  double* Bc = U;                   // N x 4 (system input order), dead before U is used
-  double* fc = U + 4 * N;           // N
-  for (int i = t; i < lay.lr_end - lay.region; i += TPC) scr[i] = 0.0;
-  for (int i = t; i < 6 * kLD; i += TPC) U[i] = 0.0;
-  if (t < 4 * N) Cc[t] = 0.0;
-  group_sync(g, TPC);
 
-  // ---- phase 1: Observer::ObserveAPosteriori (observer.cc:24-40), with the C of the
-  //      previous linearisation (same x_hat) ------------------------------------------------
+  // ---- load: linearisation from K0, delay-line contents, measurement -----------------------
+  // every matrix slot of the region (powers, L, R, V) is cleared: operands are read zero-padded
+  for (int i = t; i < lay.lr_end - lay.region; i += TPC) {
+    double v = 0.0;
+    if (i < kNNP) v = wk[kWAc + i];
+    else if (i >= 4 * kNNP && i < 5 * kNNP) v = wk[kWXc + i - 4 * kNNP];
+    scr[i] = v;
+  }
+  if (t < 4 * N) Cc[t] = wk[kWCc + t];
+  if (t < 6 * kLD) U[t] = 0.0;
+  if (t < 4) {
+    yv[t] = y[size_t(scen) * 4 + t];
+    dxd[t] = gs[kOffDx + N + t];
+  }
   // delay-line contents relative to u_old (AdjustAllDelayedStates, aug_lin_sys.h:141-154)
   for (int i = t; i < 2 * kDelay; i += TPC) {
     const int d = i / kDelay, tt = i % kDelay;
     const int slot = (tt == 0) ? (NOBS + d) : (NOBS + 2 + d * (kDelay - 1) + tt - 1);
-    q[i] = dx[slot] - uold[1 + 2 * d];
+    q[i] = gs[kOffDx + slot] - gs[kOffUold + 1 + 2 * d];
   }
-  if (t < 4) ev[t] = yv[t] - yold[t] - (plant_c_row_dot<S::PLANT>(xh, t, dx) + dx[N + t]);
-  group_sync(g, TPC);
-  double xh_new = 0.0;
-  if (t < NOBS) {
-    double acc = dx[t];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) acc = fma(cp.M[t * 4 + r], ev[r], acc);
-    if (t < N) xh_new = xh[t] + acc;  // x_ += ObserveAPosteriori(y)  (distributed_controller.cc:80)
-    dx[t] = acc;
-  }
-  group_sync(g, TPC);  // everyone has read the old xh/dx
-  if (t < N) xh[t] = xh_new;
-  group_sync(g, TPC);
-
-  // ---- phase 2: linearise at (x_hat, u_full_old)  (aug_lin_sys.cc:147); three threads ------
-  if (t < 3) plant_linearize_part<S::PLANT>(t, xh, ufull, Ac, kLD, Bc, Cc, fc);
   group_sync(g, TPC);
 
   // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) on the FP64 tensor cores -------------
@@ -306,12 +342,6 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
     mma3(c1, a, b1);
     tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0);
     tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1);
-    // [Bd | fd] source with Bd's columns permuted into this controller's input order
-    // (aug_lin_sys.cc:156-173)
-    for (int idx = t; idx < N * 5; idx += TPC) {
-      const int i = idx / 5, cc = idx % 5;
-      Xc[i * kLD + cc] = (cc < 4) ? Bc[i * 4 + cp.ctrl_idx[cc]] : fc[i];
-    }
     group_sync(g, TPC);
     frag_a(A2, kLD, mt_w, lane, a);
     mma3(c0, a, b0);
@@ -607,7 +637,7 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
         }
         const int oy = cp.out_idx[y];
         const double yref = P.yref[(size_t(g) * p + r) * NY + y];
-        wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dx[N + oy] + conv[j][y] - (yref - yv[oy]);
+        wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dxd[oy] + conv[j][y] - (yref - yv[oy]);
       }
 #pragma unroll
       for (int c = 0; c < NSC; ++c) off[c] += gv[c];
@@ -647,7 +677,6 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
 #pragma unroll
     for (int i = 0; i < S::NACC; ++i) red[t * RS + i] = acc[i];
     group_sync(g, TPC);
-    // qpm: H (NV*NV) | f (NV) | Gx (NV*NVO)
     if (t < S::NACC) {
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
@@ -662,280 +691,231 @@ __device__ void control_step(const StepParams& P, const DeviceState& G, int scen
         const int b = a + rem;
         double hv = v;
         if (a / NU == b / NU) hv += cp.R[(a % NU) * NU + (b % NU)];  // u_weight_ = I_m (x) uwt
-        qpm[a * NV + b] = hv;
-        qpm[b * NV + a] = hv;
         double* gH = G.qpH + (size_t(scen) * S::NCTRL + g) * NV * NV;
         gH[a * NV + b] = hv;
         gH[b * NV + a] = hv;
       } else if (t < NH + NV * NVO) {
-        qpm[NV * NV + NV + (t - NH)] = v;
         G.qpG[(size_t(scen) * S::NCTRL + g) * NV * (NVO > 0 ? NVO : 1) + (t - NH)] = v;
       } else {
         const int v_i = t - NH - NV * NVO;
-        qpm[NV * NV + v_i] = v;
         G.qpf[(size_t(scen) * S::NCTRL + g) * NV + v_i] = v;
       }
     }
   }
-  __syncthreads();
+  // [Bd | fd] for the a-priori observer update in K2
+  for (int i = t; i < N * kNC; i += TPC) wk[kWBF + i] = BF[i];
+}
 
-  // ---- phase 8: n_iter Jacobi sweeps (nerve_center.h:146-158,275-296) ----------------------
-  if constexpr (NV == 4 && S::NCTRL == 2) {
-    // warp 0: 16 lanes per sub-controller, everything in registers (qp_warp.cuh)
-    if (threadIdx.x < 32) {
-      const int ln = threadIdx.x;
-      QpLane QL;
-      QL.half = ln >> 4; QL.i = (ln >> 2) & 3; QL.j = ln & 3; QL.base = ln & 16;
-      const int c = QL.half;
-      const double* qm = smem + c * lay.total + lay.qp;
-      const double* uo = smem + c * lay.total + lay.uold;
-      const CtrlParams& cq = P.c[c];
-      const double Hij = qm[QL.i * 4 + QL.j];
-      const double Gij = qm[NV * NV + NV + QL.i * 4 + QL.j];
-      const double f0 = qm[NV * NV + QL.i];
-      // right-hand side of this lane's own constraint (kind = i, variable = j), a'z >= b form
-      double bnd;
-      {
-        const int iu = QL.j & 1;
-        const double lo = cq.lower[iu] - uo[iu], up = cq.upper[iu] - uo[iu];
-        bnd = (QL.i == 0) ? lo : (QL.i == 1) ? -up : (QL.i == 2) ? cq.rate_lower[iu] : -cq.rate_upper[iu];
-      }
-      bool pd;
-      const double J = qw_inverse(Hij, QL, &pd);
-      unsigned wset = G.guess[size_t(scen) * 2 + c];
-      if (wset == kQpNoGuess) wset = 0;          // no warm start: begin from the unconstrained minimiser
-      QpReduced red;
-      bool red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
-      double z_col = ss[4 + c * NV + QL.j];      // du_prev = du_old_ (own plan, entry j)
-      double x_row = 0.0, lam_row = 0.0, f_row = f0;
-      int status = pd ? 0 : 3;
-      for (int it = 0; it < P.n_iter; ++it) {
-        const double zo = __shfl_xor_sync(kFullMask, z_col, 16);   // the other controller's previous plan
-        f_row = f0 + qw_row_sum(Gij * zo);
-        bool ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
-        const bool need_slow = pd && !ok;
-        if (__any_sync(kFullMask, need_slow)) {
-          // the working set changes (rare): lane 0 of the half runs the general dual active-set
-          // solver, the half rebuilds its reduced system for the new set
-          double fi[4];
+// ---- K2: Jacobi sweeps (nerve_center.h:146-158,275-296), first move (nerve_center.h:162-167,
+// 313-319), UpdateU / ObserveAPriori (distributed_controller.h:146-152, observer.cc:6-19).
+// One warp per scenario.
+template <class S>
+__global__ void __launch_bounds__(128)
+solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+  constexpr int N = S::N, NU = S::NU, NV = S::NV, NVO = S::NVO, NTOT = S::NTOT, NOBS = S::NOBS;
+  constexpr int NCTRL = S::NCTRL;
+  const int ln = threadIdx.x & 31;
+  const int scen = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (scen >= P.batch) return;
+  double* ss = G.scen + size_t(scen) * kScenStateStride;
+  const size_t sc0 = size_t(scen) * NCTRL;
+  // first moves of every controller, system input order (valid on all lanes after the sweeps)
+  double du_sys[4] = {0.0, 0.0, 0.0, 0.0};
+
+  if constexpr (NV == 4 && NCTRL == 2) {
+    // 16 lanes per sub-controller, everything in registers (qp_warp.cuh)
+    QpLane QL;
+    QL.half = ln >> 4; QL.i = (ln >> 2) & 3; QL.j = ln & 3; QL.base = ln & 16;
+    const int c = QL.half;
+    const double* gH = G.qpH + (sc0 + c) * NV * NV;
+    const double* gf = G.qpf + (sc0 + c) * NV;
+    const double* gG = G.qpG + (sc0 + c) * NV * NVO;
+    const double* uo = G.ctrl + (sc0 + c) * kCtrlStateStride + kOffUold;
+    const CtrlParams& cq = P.c[c];
+    unsigned wset = G.guess[sc0 + c];
+    const double Hij = gH[QL.i * 4 + QL.j];
+    const double Gij = gG[QL.i * 4 + QL.j];
+    const double f0 = gf[QL.i];
+    double z_col = ss[4 + c * NV + QL.j];      // du_prev = du_old_ (own plan, entry j)
+    // right-hand side of this lane's own constraint (kind = i, variable = j), a'z >= b form
+    double bnd;
+    {
+      const int iu = QL.j & 1;
+      const double uold = uo[iu];
+      const double lo = cq.lower[iu] - uold, up = cq.upper[iu] - uold;
+      bnd = (QL.i == 0) ? lo : (QL.i == 1) ? -up : (QL.i == 2) ? cq.rate_lower[iu] : -cq.rate_upper[iu];
+    }
+    bool pd;
+    const double J = qw_inverse(Hij, QL, &pd);
+    if (wset == kQpNoGuess) wset = 0;          // no warm start: begin from the unconstrained minimiser
+    QpReduced red;
+    bool red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
+    double x_row = 0.0, lam_row = 0.0, f_row = f0;
+    int status = pd ? 0 : 3;
+    for (int it = 0; it < P.n_iter; ++it) {
+      const double zo = __shfl_xor_sync(kFullMask, z_col, 16);   // the other controller's previous plan
+      f_row = f0 + qw_row_sum(Gij * zo);
+      bool ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
+      const bool need_slow = pd && !ok;
+      if (__any_sync(kFullMask, need_slow)) {
+        // the working set changes (rare): lane 0 of the half runs the general dual active-set
+        // solver, the half rebuilds its reduced system for the new set
+        double fi[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) fi[k] = qw_get(f_row, QL, k, 0);
-          unsigned new_w = wset;
-          int st = 0;
-          if (need_slow && ln == QL.base) {
-            QpData<4> qd;
+        for (int k = 0; k < 4; ++k) fi[k] = qw_get(f_row, QL, k, 0);
+        unsigned new_w = wset;
+        int st = 0;
+        if (need_slow && ln == QL.base) {
+          QpData<4> qd;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              qd.lb[k] = cq.lower[k & 1] - uo[k & 1];
-              qd.ub[k] = cq.upper[k & 1] - uo[k & 1];
-              qd.lbA[k] = cq.rate_lower[k & 1];
-              qd.ubA[k] = cq.rate_upper[k & 1];
-            }
-            double zs[4], obj_;
-            unsigned act_, gset = kQpNoGuess;
-            st = qp_invert_spd<4>(qm, qd.J) ? qp_solve<4, 2>(qd, qm, fi, &gset, zs, &act_, &obj_) : 3;
-            if (st == 0) new_w = gset;
+          for (int k = 0; k < 4; ++k) {
+            qd.lb[k] = cq.lower[k & 1] - uo[k & 1];
+            qd.ub[k] = cq.upper[k & 1] - uo[k & 1];
+            qd.lbA[k] = cq.rate_lower[k & 1];
+            qd.ubA[k] = cq.rate_upper[k & 1];
           }
-          st = __shfl_sync(kFullMask, st, QL.base);
-          new_w = __shfl_sync(kFullMask, new_w, QL.base);
-          if (need_slow) {
-            status = st;
-            wset = new_w;
-          } else if (pd) {
-            status = 0;
-          }
-          red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
-          ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
-          if (need_slow && st == 0 && !ok) status = 1;   // should not happen: KKT of the new set
+          double zs[4], obj_;
+          unsigned act_, gset = kQpNoGuess;
+          st = qp_invert_spd<4>(gH, qd.J) ? qp_solve<4, 2>(qd, gH, fi, &gset, zs, &act_, &obj_) : 3;
+          if (st == 0) new_w = gset;
+        }
+        st = __shfl_sync(kFullMask, st, QL.base);
+        new_w = __shfl_sync(kFullMask, new_w, QL.base);
+        if (need_slow) {
+          status = st;
+          wset = new_w;
         } else if (pd) {
           status = 0;
         }
-        const double xj = qw_get(x_row, QL, QL.j, 0);
-        z_col = (status == 0) ? xj : 0.0;        // mpc_qp_solver.cc:66-69: zeros on failure
+        red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
+        ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
+        if (need_slow && st == 0 && !ok) status = 1;   // should not happen: KKT of the new set
+      } else if (pd) {
+        status = 0;
       }
-      if (QL.i == 0) zbuf[c * NV + QL.j] = z_col;
-      // report of the last sweep: active constraints (strictly positive multiplier), objective
-      double fmax = fabs(f_row);
-      fmax = fmax > 1.0 ? fmax : 1.0;
-      {
-        double o = __shfl_xor_sync(kFullMask, fmax, 4);
-        fmax = fmax > o ? fmax : o;
-        o = __shfl_xor_sync(kFullMask, fmax, 8);
-        fmax = fmax > o ? fmax : o;
-      }
-      const int l = ln & 15;
-      const int wpos = __popc(wset & ((1u << l) - 1u));
-      const double lam_l = __shfl_sync(kFullMask, lam_row, QL.base + 4 * (wpos & 3));
-      const bool is_act = ((wset >> l) & 1u) && lam_l > 1e-9 * fmax && status == 0;
-      const unsigned act = (__ballot_sync(kFullMask, is_act) >> QL.base) & 0xffffu;
-      const double zi = x_row;   // z[i] on row i
-      double ob = 0.5 * zi * Hij * z_col + ((QL.j == 0) ? f_row * zi : 0.0);
-      ob += __shfl_xor_sync(kFullMask, ob, 1);
-      ob += __shfl_xor_sync(kFullMask, ob, 2);
-      ob += __shfl_xor_sync(kFullMask, ob, 4);
-      ob += __shfl_xor_sync(kFullMask, ob, 8);
-      if (ln == QL.base) {
-        if (status == 0) G.guess[size_t(scen) * 2 + c] = wset;
-        G.status[size_t(scen) * 2 + c] = status;
-        G.active[size_t(scen) * 2 + c] = status == 0 ? act : 0u;
-        G.objective[size_t(scen) * 2 + c] = status == 0 ? ob : 0.0;
-      }
+      const double xj = qw_get(x_row, QL, QL.j, 0);
+      z_col = (status == 0) ? xj : 0.0;        // mpc_qp_solver.cc:66-69: zeros on failure
     }
+    // report of the last sweep: active constraints (strictly positive multiplier), objective
+    double fmax = fabs(f_row);
+    fmax = fmax > 1.0 ? fmax : 1.0;
+    {
+      double o = __shfl_xor_sync(kFullMask, fmax, 4);
+      fmax = fmax > o ? fmax : o;
+      o = __shfl_xor_sync(kFullMask, fmax, 8);
+      fmax = fmax > o ? fmax : o;
+    }
+    const int l = ln & 15;
+    const int wpos = __popc(wset & ((1u << l) - 1u));
+    const double lam_l = __shfl_sync(kFullMask, lam_row, QL.base + 4 * (wpos & 3));
+    const bool is_act = ((wset >> l) & 1u) && lam_l > 1e-9 * fmax && status == 0;
+    const unsigned act = (__ballot_sync(kFullMask, is_act) >> QL.base) & 0xffffu;
+    double ob = 0.5 * x_row * Hij * z_col + ((QL.j == 0) ? f_row * x_row : 0.0);
+    ob += __shfl_xor_sync(kFullMask, ob, 1);
+    ob += __shfl_xor_sync(kFullMask, ob, 2);
+    ob += __shfl_xor_sync(kFullMask, ob, 4);
+    ob += __shfl_xor_sync(kFullMask, ob, 8);
+    if (ln == QL.base) {
+      if (status == 0) G.guess[sc0 + c] = wset;
+      G.status[sc0 + c] = status;
+      G.active[sc0 + c] = status == 0 ? act : 0u;
+      G.objective[sc0 + c] = status == 0 ? ob : 0.0;
+    }
+    // du_old_ = du_prev (full plans); first moves in system order = [ctrl 0: z0 z1 | ctrl 1: z0 z1]
+    if (QL.i == 0) ss[4 + c * NV + QL.j] = z_col;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) du_sys[k] = __shfl_sync(kFullMask, z_col, 16 * (k >> 1) + (k & 1));
   } else {
-    // lane c of warp 0 owns sub-controller c; plans are exchanged through zbuf.
-  if (threadIdx.x < 32) {
-    const int c = threadIdx.x;
-    const bool on = c < S::NCTRL;
-    QpData<NV> qd;
-    double f0[NV], z[NV], lam[NV], fi[NV];
-    unsigned wset = kQpNoGuess, act = 0;
-    double obj = 0.0;
-    int status = 0, nq = 0;
-    bool pd = true, fast_ok = false;
-    const double* qm = smem + (on ? c : 0) * lay.total + lay.qp;
-    double* fast = smem + (on ? c : 0) * lay.total + lay.qp + NV * NV + NV + NV * (NVO > 0 ? NVO : 1);
+    // generic path (centralised, 8 variables): lane c owns sub-controller c
+    const int c = ln;
+    const bool on = c < NCTRL;
+    double z[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) z[i] = 0.0;
     if (on) {
-      const double* uo = smem + c * lay.total + lay.uold;
+      const double* gH = G.qpH + (sc0 + c) * NV * NV;
+      const double* gf = G.qpf + (sc0 + c) * NV;
+      const double* uo = G.ctrl + (sc0 + c) * kCtrlStateStride + kOffUold;
       const CtrlParams& cq = P.c[c];
+      QpData<NV> qd;
+      double f0[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        f0[i] = qm[NV * NV + i];
-        z[i] = 0.0;
+        f0[i] = gf[i];
         qd.lb[i] = cq.lower[i % NU] - uo[i % NU];
         qd.ub[i] = cq.upper[i % NU] - uo[i % NU];
         qd.lbA[i] = cq.rate_lower[i % NU];
         qd.ubA[i] = cq.rate_upper[i % NU];
       }
-      pd = qp_invert_spd<NV>(qm, qd.J);
-      wset = G.guess[size_t(scen) * S::NCTRL + c];
-      if (pd && wset != kQpNoGuess) fast_ok = qp_prepare<NV, NU>(qd, wset, fast, &nq);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) zbuf[c * NV + i] = ss[4 + c * NV + i];  // du_prev = du_old_
-    }
-    __syncwarp();
-    for (int it = 0; it < P.n_iter; ++it) {
-      if (on) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) fi[i] = f0[i];
-        if (NVO > 0) {
-          const double* zo = zbuf + (1 - c) * NV;  // the other controller's previous plan
-          const double* Gx = qm + NV * NV + NV;
-#pragma unroll
-          for (int i = 0; i < NV; ++i)
-#pragma unroll
-            for (int k = 0; k < NVO; ++k) fi[i] = fma(Gx[i * NVO + k], zo[k], fi[i]);
-        }
-        if (!pd) {
-          status = 3;
-        } else if (fast_ok && qp_eval_fast<NV, NU>(qd, fast, nq, wset, fi, z, lam)) {
-          status = 0;
-        } else {
-          // the working set changes (rare): general dual active-set solve, then re-prepare
-          unsigned gset = wset;
-          status = qp_solve<NV, NU>(qd, qm, fi, &gset, z, &act, &obj);
-          if (status == 0) {
-            wset = gset;
-            fast_ok = qp_prepare<NV, NU>(qd, wset, fast, &nq);
-            // multipliers of the new working set for the report below
-            if (fast_ok) qp_eval_fast<NV, NU>(qd, fast, nq, wset, fi, z, lam);
-          } else {
-            fast_ok = false;
-          }
-        }
-        if (status != 0) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) z[i] = 0.0;   // mpc_qp_solver.cc:66-69
-        }
+      unsigned wset = G.guess[sc0 + c], act = 0;
+      double obj = 0.0;
+      int status = 3;
+      if (qp_invert_spd<NV>(gH, qd.J)) {
+        // a single controller has no plan to exchange: every sweep solves the same QP
+        // (distributed_controller.h:215-218), so one solve gives the result of all n_iter sweeps
+        static_assert(NVO == 0, "generic path is the centralised controller");
+        status = qp_solve<NV, NU>(qd, gH, f0, &wset, z, &act, &obj);
       }
-      __syncwarp();
-      if (on) {
+      if (status != 0) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) zbuf[c * NV + i] = z[i];
-      }
-      __syncwarp();
-    }
-    if (on) {
-      if (status == 0) {
-        // report of the last sweep: active constraints (strictly positive multiplier), objective
-        double fmax = 1.0;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) fmax = fmax > fabs(fi[i]) ? fmax : fabs(fi[i]);
-        act = 0;
-        int w = 0;
-        for (int j = 0; j < 4 * NV; ++j)
-          if ((wset >> j) & 1u) {
-            if (wset != kQpNoGuess && lam[w] > 1e-9 * fmax) act |= 1u << j;
-            ++w;
-          }
-        obj = 0.0;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k < NV; ++k) s = fma(qm[i * NV + k], z[k], s);
-          obj += z[i] * (0.5 * s + fi[i]);
-        }
-        G.guess[size_t(scen) * S::NCTRL + c] = wset;
+        for (int i = 0; i < NV; ++i) z[i] = 0.0;
       } else {
-        act = 0;
-        obj = 0.0;
+        G.guess[sc0 + c] = wset;
       }
-      G.status[size_t(scen) * S::NCTRL + c] = status;
-      G.active[size_t(scen) * S::NCTRL + c] = act;
-      G.objective[size_t(scen) * S::NCTRL + c] = obj;
-    }
-  }
-  }
-  __syncthreads();
-
-  // ---- phase 9: apply first move, UpdateU / ObserveAPriori (observer.cc:6-19) --------------
-  {
-    double du[4] = {0.0, 0.0, 0.0, 0.0};
+      G.status[sc0 + c] = status;
+      G.active[sc0 + c] = status == 0 ? act : 0u;
+      G.objective[sc0 + c] = status == 0 ? obj : 0.0;
 #pragma unroll
-    for (int i = 0; i < NU; ++i) du[i] = zbuf[g * NV + i];
-    const double h0 = dx[NOBS + 0] - uold[1], h1 = dx[NOBS + 1] - uold[3];
-    for (int i = t; i < NTOT; i += TPC) {
-      double v;
+      for (int i = 0; i < NV; ++i) ss[4 + c * NV + i] = z[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) du_sys[k] = __shfl_sync(kFullMask, z[k < NU ? k : 0], 0);
+  }
+
+  // nerve_center.h:162-167,313-319: u_old_ += first move of each controller's plan
+  if (ln < 4) {
+    const double un = ss[ln] + du_sys[ln];
+    u[size_t(scen) * 4 + ln] = un;
+    ss[ln] = un;
+  }
+  // UpdateU / ObserveAPriori for every controller: each sees only its own inputs move
+  // (nerve_center.h:322-328); lanes split the augmented state
+  for (int c = 0; c < NCTRL; ++c) {
+    double* gs = G.ctrl + (sc0 + c) * kCtrlStateStride;
+    const double* BF = G.work + (sc0 + c) * kWorkStride + kWBF;
+    double du[4] = {0.0, 0.0, 0.0, 0.0}, uold[4];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) du[i] = du_sys[c * NU + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) uold[i] = gs[kOffUold + i];
+    const double h0 = gs[kOffDx + NOBS + 0] - uold[1], h1 = gs[kOffDx + NOBS + 1] - uold[3];
+    constexpr int PER = (NTOT + 31) / 32;
+    double nv[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = ln + 32 * k;
+      double v = 0.0;
       if (i < N) {
         v = BF[i * kNC + 0] * du[0] + BF[i * kNC + 2] * du[2] + BF[i * kNC + 1] * h0 +
             BF[i * kNC + 3] * h1 + BF[i * kNC + 4];
       } else if (i < NOBS) {
-        v = dx[i];
+        v = gs[kOffDx + i];
       } else if (i < NOBS + 2) {
-        v = dx[NOBS + 2 + (i - NOBS) * (kDelay - 1)];  // head <- first chain slot
-      } else {
+        v = gs[kOffDx + NOBS + 2 + (i - NOBS) * (kDelay - 1)];  // head <- first chain slot
+      } else if (i < NTOT) {
         const int cidx = i - NOBS - 2, d = cidx / (kDelay - 1), jj = cidx % (kDelay - 1);
-        v = (jj == kDelay - 2) ? uold[1 + 2 * d] + du[1 + 2 * d] : dx[i + 1];
+        v = (jj == kDelay - 2) ? uold[1 + 2 * d] + du[1 + 2 * d] : gs[kOffDx + i + 1];
       }
-      gs[kOffDx + i] = v;
+      nv[k] = v;
     }
-    if (t < N) gs[kOffXhat + t] = xh[t];
-    if (t < 4) {
-      gs[kOffYold + t] = yv[t];
-      gs[kOffUold + t] = uold[t] + du[t];
+    __syncwarp();   // every lane has read the old delay line before anyone overwrites it
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = ln + 32 * k;
+      if (i < NTOT) gs[kOffDx + i] = nv[k];
     }
+    if (ln < 4) gs[kOffUold + ln] = uold[ln] + du[ln];
   }
-  if (threadIdx.x < 4) {
-    // nerve_center.h:162-167,313-319: u_old_ += first move of each controller's plan
-    const int c = threadIdx.x / NU, i = threadIdx.x % NU;
-    const double un = ss[threadIdx.x] + zbuf[c * NV + i];
-    u_out[threadIdx.x] = un;
-    ss[threadIdx.x] = un;
-  }
-  if (threadIdx.x < S::NCTRL * NV) ss[4 + threadIdx.x] = zbuf[threadIdx.x];  // du_old_ = du_prev
-}
-
-#ifndef CMPC_MIN_BLOCKS
-#define CMPC_MIN_BLOCKS 3
-#endif
-
-template <class S, int RPT>
-__global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
-step_kernel(StepParams P, DeviceState G, const double* __restrict__ y, double* __restrict__ u) {
-  extern __shared__ __align__(16) double smem[];
-  const int scen = blockIdx.x;
-  if (scen >= P.batch) return;
-  control_step<S, RPT>(P, G, scen, y + size_t(scen) * 4, u + size_t(scen) * 4, smem);
 }
 
 }  // namespace cmpc

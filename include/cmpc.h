@@ -120,11 +120,15 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
                                 const double* block_off_dev, double* traj_dev,
                                 uint32_t* qp_active_dev, double* qp_objective_dev,
                                 int32_t* qp_status_dev, void* stream);
-/* Per-kernel device timing: when on, every control-step kernel launch is bracketed by CUDA
- * events on its stream; cmpc_get_timing synchronises, returns the number of timed launches and
- * their summed duration, and resets the counters. */
+/* Per-kernel device timing: when on, every control step (its three kernels: linearise, assemble,
+ * solve) is bracketed by CUDA events on its stream; cmpc_get_timing synchronises, returns the
+ * number of timed control steps, the summed duration of whole control steps and of their
+ * assemble kernels alone, and resets the counters. */
 int cmpc_set_timing(cmpc_handle* h, int on);
-int cmpc_get_timing(cmpc_handle* h, int64_t* n_step_launches, double* step_kernel_ms);
+int cmpc_get_timing(cmpc_handle* h, int64_t* n_steps, double* step_ms, double* assemble_ms);
+/* Developer aid: per-scenario clock64() stamps of the control-step phases of the last launch
+ * (B x 16 int64; only filled by builds with -DCMPC_PHASE_TIMING, zeros otherwise). */
+int cmpc_debug_phase_ticks(cmpc_handle* h, long long* out);
 /* Number of kernel launches issued by this handle so far (for bench accounting). */
 int cmpc_launch_count(cmpc_handle* h, int64_t* n_launches);
 
