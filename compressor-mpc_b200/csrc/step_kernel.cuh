@@ -236,7 +236,6 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int part = tid & 3, quad = tid >> 2;
   const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
   if (scen >= P.batch) return;
-  const CtrlParams& cp = P.c[g];
   double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   const double* ss = G.scen + size_t(scen) * kScenStateStride;
   double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
@@ -254,7 +253,7 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   for (int i = 0; i < NOBS; ++i) {
     double acc = dx[i];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc = fma(cp.M[i * 4 + r], ev[r], acc);
+    for (int r = 0; r < 4; ++r) acc = fma(P.c[g].M[i * 4 + r], ev[r], acc);
     dx[i] = acc;
   }
 #pragma unroll
@@ -275,7 +274,7 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   uf[0] += ss[0]; uf[3] += ss[1]; uf[4] += ss[2]; uf[7] += ss[3];
   int inv[4];   // system control input -> this controller's local input (aug_lin_sys.cc:156-173)
 #pragma unroll
-  for (int c = 0; c < 4; ++c) inv[cp.ctrl_idx[c]] = c;
+  for (int c = 0; c < 4; ++c) inv[P.c[g].ctrl_idx[c]] = c;
   plant_linearize_part_x<S::PLANT>(part, xh, uf, wk + kWAc, kLD, wk + kWXc, kLD, inv, wk + kWCc);
 }
 
@@ -293,7 +292,6 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int p = P.p, b_max = P.b_max, ldr = P.ldr;
   const SmemLayout<S> lay(p, b_max, P.n_pow);
   double* sm = smem + g * lay.total;
-  const CtrlParams& cp = P.c[g];
   const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
 
@@ -308,25 +306,47 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   double* Xc = scr + 4 * kNNP;      // [Bc (local input order) | fc], N x 5, stride kLD
 
   // ---- load: linearisation from K0, delay-line contents, measurement -----------------------
-  // every matrix slot of the region (powers, L, R, V) is cleared: operands are read zero-padded
-  for (int i = t; i < lay.lr_end - lay.region; i += TPC) {
-    double v = 0.0;
-    if (i < kNNP) v = wk[kWAc + i];
-    else if (i >= 4 * kNNP && i < 5 * kNNP) v = wk[kWXc + i - 4 * kNNP];
-    scr[i] = v;
-  }
-  if (t < 4 * N) Cc[t] = wk[kWCc + t];
-  if (t < 6 * kLD) U[t] = 0.0;
-  if (t < 4) {
-    yv[t] = y[size_t(scen) * 4 + t];
-    dxd[t] = gs[kOffDx + N + t];
+  // all global loads are issued first so that they are in flight together
+  constexpr int NLD = (kNNP + TPC - 1) / TPC;
+  double a_v[NLD], x_v[NLD], q_v[2], cc_v = 0.0, yd_v = 0.0;
+#pragma unroll
+  for (int k = 0; k < NLD; ++k) {
+    const int i = t + k * TPC;
+    a_v[k] = (i < kNNP) ? wk[kWAc + i] : 0.0;
+    x_v[k] = (i < kNNP) ? wk[kWXc + i] : 0.0;
   }
   // delay-line contents relative to u_old (AdjustAllDelayedStates, aug_lin_sys.h:141-154)
-  for (int i = t; i < 2 * kDelay; i += TPC) {
-    const int d = i / kDelay, tt = i % kDelay;
-    const int slot = (tt == 0) ? (NOBS + d) : (NOBS + 2 + d * (kDelay - 1) + tt - 1);
-    q[i] = gs[kOffDx + slot] - gs[kOffUold + 1 + 2 * d];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = t + k * TPC;
+    q_v[k] = 0.0;
+    if (i < 2 * kDelay) {
+      const int d = i / kDelay, tt = i % kDelay;
+      const int slot = (tt == 0) ? (NOBS + d) : (NOBS + 2 + d * (kDelay - 1) + tt - 1);
+      q_v[k] = gs[kOffDx + slot] - gs[kOffUold + 1 + 2 * d];
+    }
   }
+  if (t < 4 * N) cc_v = wk[kWCc + t];
+  if (t < 4) yd_v = y[size_t(scen) * 4 + t];
+  else if (t < 8) yd_v = gs[kOffDx + N + t - 4];
+  // every matrix slot of the region (powers, L, R, V) is cleared: operands are read zero-padded
+  for (int i = t + 5 * kNNP; i < lay.lr_end - lay.region; i += TPC) scr[i] = 0.0;
+  for (int i = t + kNNP; i < 4 * kNNP; i += TPC) scr[i] = 0.0;
+  if (t < 6 * kLD) U[t] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NLD; ++k) {
+    const int i = t + k * TPC;
+    if (i < kNNP) {
+      Ac[i] = a_v[k];
+      Xc[i] = x_v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (t + k * TPC < 2 * kDelay) q[t + k * TPC] = q_v[k];
+  if (t < 4 * N) Cc[t] = cc_v;
+  if (t < 4) yv[t] = yd_v;
+  else if (t < 8) dxd[t - 4] = yd_v;
   group_sync(g, TPC);
 
   // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) on the FP64 tensor cores -------------
@@ -381,7 +401,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // R_b = Ad^(8b) [Bd fd X40]: blocks [2^j, 2^(j+1)) = Ad^(8*2^j) * blocks [0, 2^j), j = 0..
   // X40 = state reached after the 40 queued delayed inputs have been applied (free response
   // of the delay line): conv[r] = C~ Ad^(r-39) X40 for r >= 39 comes out of the same table.
-  for (int idx = t; idx < NY * N; idx += TPC) L[(idx / N) * kLD + idx % N] = Cc[cp.out_idx[idx / N] * N + idx % N];
+  for (int idx = t; idx < NY * N; idx += TPC) L[(idx / N) * kLD + idx % N] = Cc[P.c[g].out_idx[idx / N] * N + idx % N];
   for (int idx = t; idx < N * 5; idx += TPC) R[(idx / 5) * ldr + idx % 5] = BF[(idx / 5) * kNC + idx % 5];
   for (int idx = t; idx < N * 2; idx += TPC) V[(idx >> 1) * kLDV + (idx & 1)] = BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)];
   group_sync(g, TPC);
@@ -635,7 +655,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
             so[y][NO + i - NU] = off[y * kNS + i];
           }
         }
-        const int oy = cp.out_idx[y];
+        const int oy = P.c[g].out_idx[y];
         const double yref = P.yref[(size_t(g) * p + r) * NY + y];
         wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dxd[oy] + conv[j][y] - (yref - yv[oy]);
       }
@@ -647,7 +667,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         for (int v = 0; v < NV; ++v) {
           double s = 0.0;
 #pragma unroll
-          for (int y2 = 0; y2 < NY; ++y2) s = fma(cp.Q[y * NY + y2], su[y2][v], s);
+          for (int y2 = 0; y2 < NY; ++y2) s = fma(P.c[g].Q[y * NY + y2], su[y2][v], s);
           qs[y][v] = s;
         }
       int hi = 0;
@@ -690,7 +710,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         while (rem >= NV - a) { rem -= NV - a; ++a; }
         const int b = a + rem;
         double hv = v;
-        if (a / NU == b / NU) hv += cp.R[(a % NU) * NU + (b % NU)];  // u_weight_ = I_m (x) uwt
+        if (a / NU == b / NU) hv += P.c[g].R[(a % NU) * NU + (b % NU)];  // u_weight_ = I_m (x) uwt
         double* gH = G.qpH + (size_t(scen) * S::NCTRL + g) * NV * NV;
         gH[a * NV + b] = hv;
         gH[b * NV + a] = hv;
@@ -706,11 +726,35 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   for (int i = t; i < N * kNC; i += TPC) wk[kWBF + i] = BF[i];
 }
 
+// General solve for one 4-variable QP when the warm-start working set is no longer optimal.
+// Kept out of line: it is rare, and its arrays must not cost the sweep loop any registers.
+// Everything is passed by value (no pointer into the kernel parameters may escape, or the
+// compiler would spill the whole parameter block to local memory in every thread).
+struct QpBounds4 {
+  double lo0, lo1, up0, up1, rlo0, rlo1, rup0, rup1;
+};
+__device__ __noinline__ int qp_fallback4(const double* H, double f0, double f1, double f2, double f3, QpBounds4 b,
+                                         unsigned* wset_out) {
+  QpData<4> qd;
+  qd.lb[0] = qd.lb[2] = b.lo0; qd.lb[1] = qd.lb[3] = b.lo1;
+  qd.ub[0] = qd.ub[2] = b.up0; qd.ub[1] = qd.ub[3] = b.up1;
+  qd.lbA[0] = qd.lbA[2] = b.rlo0; qd.lbA[1] = qd.lbA[3] = b.rlo1;
+  qd.ubA[0] = qd.ubA[2] = b.rup0; qd.ubA[1] = qd.ubA[3] = b.rup1;
+  double fi[4] = {f0, f1, f2, f3}, zs[4], obj_;
+  unsigned act_, gset = kQpNoGuess;
+  const int st = qp_invert_spd<4>(H, qd.J) ? qp_solve<4, 2>(qd, H, fi, &gset, zs, &act_, &obj_) : 3;
+  if (st == 0) *wset_out = gset;
+  return st;
+}
+
 // ---- K2: Jacobi sweeps (nerve_center.h:146-158,275-296), first move (nerve_center.h:162-167,
 // 313-319), UpdateU / ObserveAPriori (distributed_controller.h:146-152, observer.cc:6-19).
 // One warp per scenario.
+#ifndef CMPC_SOLVE_MIN_BLOCKS
+#define CMPC_SOLVE_MIN_BLOCKS 3
+#endif
 template <class S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, S::NV == 4 ? CMPC_SOLVE_MIN_BLOCKS : 2)
 solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
   constexpr int N = S::N, NU = S::NU, NV = S::NV, NVO = S::NVO, NTOT = S::NTOT, NOBS = S::NOBS;
   constexpr int NCTRL = S::NCTRL;
@@ -731,7 +775,6 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     const double* gf = G.qpf + (sc0 + c) * NV;
     const double* gG = G.qpG + (sc0 + c) * NV * NVO;
     const double* uo = G.ctrl + (sc0 + c) * kCtrlStateStride + kOffUold;
-    const CtrlParams& cq = P.c[c];
     unsigned wset = G.guess[sc0 + c];
     const double Hij = gH[QL.i * 4 + QL.j];
     const double Gij = gG[QL.i * 4 + QL.j];
@@ -742,8 +785,8 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     {
       const int iu = QL.j & 1;
       const double uold = uo[iu];
-      const double lo = cq.lower[iu] - uold, up = cq.upper[iu] - uold;
-      bnd = (QL.i == 0) ? lo : (QL.i == 1) ? -up : (QL.i == 2) ? cq.rate_lower[iu] : -cq.rate_upper[iu];
+      const double lo = P.c[c].lower[iu] - uold, up = P.c[c].upper[iu] - uold;
+      bnd = (QL.i == 0) ? lo : (QL.i == 1) ? -up : (QL.i == 2) ? P.c[c].rate_lower[iu] : -P.c[c].rate_upper[iu];
     }
     bool pd;
     const double J = qw_inverse(Hij, QL, &pd);
@@ -766,18 +809,12 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
         unsigned new_w = wset;
         int st = 0;
         if (need_slow && ln == QL.base) {
-          QpData<4> qd;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            qd.lb[k] = cq.lower[k & 1] - uo[k & 1];
-            qd.ub[k] = cq.upper[k & 1] - uo[k & 1];
-            qd.lbA[k] = cq.rate_lower[k & 1];
-            qd.ubA[k] = cq.rate_upper[k & 1];
-          }
-          double zs[4], obj_;
-          unsigned act_, gset = kQpNoGuess;
-          st = qp_invert_spd<4>(gH, qd.J) ? qp_solve<4, 2>(qd, gH, fi, &gset, zs, &act_, &obj_) : 3;
-          if (st == 0) new_w = gset;
+          QpBounds4 qb;
+          qb.lo0 = P.c[c].lower[0] - uo[0]; qb.lo1 = P.c[c].lower[1] - uo[1];
+          qb.up0 = P.c[c].upper[0] - uo[0]; qb.up1 = P.c[c].upper[1] - uo[1];
+          qb.rlo0 = P.c[c].rate_lower[0]; qb.rlo1 = P.c[c].rate_lower[1];
+          qb.rup0 = P.c[c].rate_upper[0]; qb.rup1 = P.c[c].rate_upper[1];
+          st = qp_fallback4(gH, fi[0], fi[1], fi[2], fi[3], qb, &new_w);
         }
         st = __shfl_sync(kFullMask, st, QL.base);
         new_w = __shfl_sync(kFullMask, new_w, QL.base);
@@ -836,16 +873,15 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
       const double* gH = G.qpH + (sc0 + c) * NV * NV;
       const double* gf = G.qpf + (sc0 + c) * NV;
       const double* uo = G.ctrl + (sc0 + c) * kCtrlStateStride + kOffUold;
-      const CtrlParams& cq = P.c[c];
       QpData<NV> qd;
       double f0[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         f0[i] = gf[i];
-        qd.lb[i] = cq.lower[i % NU] - uo[i % NU];
-        qd.ub[i] = cq.upper[i % NU] - uo[i % NU];
-        qd.lbA[i] = cq.rate_lower[i % NU];
-        qd.ubA[i] = cq.rate_upper[i % NU];
+        qd.lb[i] = P.c[0].lower[i % NU] - uo[i % NU];
+        qd.ub[i] = P.c[0].upper[i % NU] - uo[i % NU];
+        qd.lbA[i] = P.c[0].rate_lower[i % NU];
+        qd.ubA[i] = P.c[0].rate_upper[i % NU];
       }
       unsigned wset = G.guess[sc0 + c], act = 0;
       double obj = 0.0;
