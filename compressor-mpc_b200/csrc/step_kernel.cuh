@@ -220,7 +220,7 @@ __device__ __forceinline__ double plant_c_row_dot(const double* x, int r, const 
 // One control step for the scenario owned by this CTA.  y4: the new measurement (4 doubles).
 // u_out: 4 doubles.  All threads of the CTA must call it.
 #ifndef CMPC_MIN_BLOCKS
-#define CMPC_MIN_BLOCKS 3
+#define CMPC_MIN_BLOCKS 4
 #endif
 
 // ---- K0: Observer::ObserveAPosteriori (observer.cc:24-40) with the C of the previous

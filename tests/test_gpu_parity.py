@@ -199,3 +199,52 @@ def test_constraint_stress_matches_oracle(setups, pkg, gpu_lib):
     rate_bits = 0xFF00
     assert (g["active"] & rate_bits).any(), "rate constraints never became active"
     assert len(np.unique(g["active"])) > 3
+
+
+def test_long_horizon_p200_matches_oracle(setups, pkg, gpu_lib):
+    """BASELINE configs[4] shape: cooperative-parallel with twice the prediction horizon (p = 200)."""
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T, p = 4, 260, 200
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 120
+    g = pkg.from_setup(s, batch=B, p=p).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s, p=p).run_closed_loop(x0, be, bo, T, n_threads=4)
+    n = len(x_def)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+
+
+def test_full_size_batch_properties(setups, golden, pkg, gpu_lib):
+    """BASELINE configs[3] at full size: 4096 perturbed scenarios, closed loop over the disturbance
+    onset.  Size-independent properties: every QP solved, trajectories finite and inside the input
+    constraints, scenario 0 = the reference's recorded run, duplicate scenarios give identical
+    trajectories, and a spread sample of scenarios agrees with the oracle."""
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 4096, 1300
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    x0[B - 1], be[B - 1], bo[B - 1] = x0[17], be[17], bo[17]     # a duplicate far away in the batch
+    g = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    n = len(x_def)
+    u = g["traj"][:, :, 1 + n:5 + n]
+    assert (g["status"] == 0).all()
+    assert np.isfinite(g["traj"]).all()
+    lo = np.tile(s.lower, 2); hi = np.tile(s.upper, 2)
+    assert (u >= lo - 1e-9).all() and (u <= hi + 1e-9).all()
+    du = np.diff(u, axis=1)
+    assert (du >= np.tile(s.rate_lower, 2) - 1e-9).all() and (du <= np.tile(s.rate_upper, 2) + 1e-9).all()
+    assert np.array_equal(g["traj"][B - 1], g["traj"][17]) and np.array_equal(g["active"][B - 1], g["active"][17])
+    idx = golden["coop-par/index"]; rec = golden["coop-par/records"]
+    keep = idx < T
+    tr = g["traj"][0][idx[keep]]
+    assert (np.abs(tr[:, 1:1 + n] - rec[keep, 1:1 + n]) / np.maximum(np.abs(rec[keep, 1:1 + n]), 1e-3)).max() < 1e-5
+    assert np.abs(tr[:, 1 + n:5 + n] - rec[keep, 1 + n:5 + n]).max() < 5e-6
+    sample = np.array([1, 2, 3, 500, 1023, 2048, 3000, 4094])
+    o = ol.Oracle(s).run_closed_loop(x0[sample], be[sample], bo[sample], T, n_threads=8)
+    assert rel_err(u[sample], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"][sample], o["active"])
+    assert rel_err(g["objective"][sample], o["objective"], 1e-6) < RTOL_U
+    # the perturbed scenarios do differ from each other
+    assert np.unique(np.round(u[:, -1, 0], 9)).size > B // 2
