@@ -159,7 +159,7 @@ int cmpc_solve_qp(int device, int nq, int nv, const double* H, const double* f, 
                   const double* ub, const double* lbA, const double* ubA, uint32_t* guess_io,
                   double* z, uint32_t* active, double* objective, int32_t* status);
 /* DynamicSystem::{GetDerivative,GetOutput,GetLinearizedSystem} on the device
- * (systems/*.cc): x nq x n, u nq x n_inputs -> dxdt nq x n, y nq x 4, A nq x n x n,
+ * (systems/ sources): x nq x n, u nq x n_inputs -> dxdt nq x n, y nq x 4, A nq x n x n,
  * Bc nq x n x 4, C nq x 4 x n.  Host pointers, outputs may be NULL. */
 int cmpc_plant_eval(int device, int plant, int nq, const double* x, const double* u, double* dxdt,
                     double* y, double* A, double* Bc, double* C);

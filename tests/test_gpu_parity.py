@@ -248,3 +248,45 @@ def test_full_size_batch_properties(setups, golden, pkg, gpu_lib):
     assert rel_err(g["objective"][sample], o["objective"], 1e-6) < RTOL_U
     # the perturbed scenarios do differ from each other
     assert np.unique(np.round(u[:, -1, 0], 9)).size > B // 2
+
+
+def test_setup_workflow_writes_reference_records(setups, golden, pkg, gpu_lib, tmp_path):
+    """setup file in, .dat records out: the reference's cooperative-serial workflow on the GPU."""
+    s = setups["coop-ser"]
+    f = tmp_path / "setup-coop-ser"
+    f.write_text(pkg.setupfile.format_setup(s))
+    r = pkg.workflow.run_setup(f, batch=2, out_dir=tmp_path / "serial", n_records=400)
+    assert [p.name for p in r["paths"]] == ["coop9.dat", "coop9.dat.s1"]
+    got = pkg.workflow.parse_records(r["paths"][0].read_text(), 10)
+    rec = golden["coop-ser/records"][:400]
+    assert got.shape == (400, 20)
+    assert np.allclose(got[:, 0], rec[:, 0], rtol=1e-5)
+    assert (np.abs(got[:, 1:11] - rec[:, 1:11]) / np.maximum(np.abs(rec[:, 1:11]), 1e-3)).max() < 2e-5
+    assert np.abs(got[:, 11:15] - rec[:, 11:15]).max() < 1e-5
+    assert (got[:, -1] > 0).all()
+
+
+def test_cxx_setup_driver_matches_reference_records(setups, golden, pkg, gpu_lib, tmp_path):
+    """The C++ host side (reference-named facade + setup-file driver) end to end: setup file in,
+    the reference's centralized-serial .dat records out."""
+    import subprocess
+    from conftest import ROOT
+    exe = ROOT / "compressor-mpc_b200" / "cmpc_run_setup"
+    assert exe.exists(), "build with __graft_entry__.build()"
+    s = setups["cent-ser"]
+    import copy
+    s = copy.deepcopy(s)
+    s.sim_t_end = np.array([10.0, 20.0])          # 400 records instead of 10 000
+    (tmp_path / "serial").mkdir()
+    (tmp_path / "setup-cent-ser").write_text(pkg.setupfile.format_setup(s))
+    out = subprocess.run([str(exe), "setup-cent-ser", "serial", "centralized"], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = pkg.workflow.parse_records((tmp_path / "serial" / "centralized.dat").read_text(), 10)
+    T = got.shape[0]
+    assert T == 400
+    # the first 200 records are disturbance free exactly like the reference's first block
+    rec = golden["cent-ser/records"][:200]
+    assert (np.abs(got[:200, 1:11] - rec[:, 1:11]) / np.maximum(np.abs(rec[:, 1:11]), 1e-3)).max() < 2e-5
+    assert np.abs(got[:200, 11:15] - rec[:, 11:15]).max() < 1e-5
+    # after record 200 the -0.1 offset on plant input 6 (second outlet valve) acts on its outlet pressure
+    assert abs(got[-1, 7] - got[199, 7]) > 1e-3

@@ -131,3 +131,29 @@ def test_two_rank_shard_and_gather_gloo(pkg, setups, tmp_path):
     ref = ol.Oracle(s).run_closed_loop(x0, be, bo, 25)["traj"][:, -1, :]
     assert np.array_equal(got, ref)
     assert np.load(tmp_path / "tmax.npy")[0] == 2.0
+
+
+def test_dat_record_format_roundtrip(pkg, golden):
+    """The .dat writer prints records the way the reference does (6 significant digits, Eigen row
+    format) and the reference's reader (whitespace separated numbers) gets them back."""
+    wf = pkg.workflow
+    rec = golden["coop-par/records"][:50]
+    text = wf.format_records(rec, 11, 1176270)
+    first = text.splitlines()[:6]
+    assert first[0] == "0"
+    assert first[1] == "0.916 1.145 0.152   440     0 0.916 1.145 0.152   440     0  1.12"   # as in results/parallel/run1/coop9.dat
+    assert first[2] == "-4.48036e-05            0 -4.48036e-05            0"
+    assert first[4] == "1176270" and first[5] == ""
+    back = wf.parse_records(text, 11)
+    assert back.shape == (50, 21) and np.allclose(back[:, :-1], rec, rtol=1e-5, atol=1e-12)
+    assert wf.infer_test("folder-name\nserial\noutput-filename\nncoop9.dat\n") == (1, 2)
+    assert wf.infer_test("folder-name\nparallel\noutput-filename\ncentralized.dat\n") == (0, 0)
+
+
+def test_cxx_driver_built_and_reports_usage():
+    import subprocess
+    exe = ROOT / "compressor-mpc_b200" / "cmpc_run_setup"
+    if not exe.exists():
+        subprocess.check_call(["make", "-C", str(ROOT / "compressor-mpc_b200")])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
