@@ -156,7 +156,7 @@ struct SmemLayout {
 // ---- FP64 tensor-core tiles -----------------------------------------------------------------
 // D(8x8) += A(8x4) * B(4x8), one warp.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)+{0,1}].
 __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
@@ -184,6 +184,30 @@ __device__ __forceinline__ void mma3(double (&c)[2], const double (&a)[3], const
   dmma_884(c, a[1], b[1]);
   dmma_884(c, a[2], b[2]);
 }
+// NT independent tiles sharing the A fragments (one row block times NT column blocks): the DMMAs
+// of different tiles are interleaved so that no instruction waits for the previous one.
+template <int NT>
+__device__ __forceinline__ void mma3_shared_a(double (&c)[NT][2], const double (&a)[3], const double (&b)[NT][3], int n_on = NT) {
+#pragma unroll
+  for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+      if (i < n_on) dmma_884(c[i], a[kt], b[i][kt]);
+}
+// NT independent tiles sharing the B fragments (NT row blocks times one column block)
+template <int NT>
+__device__ __forceinline__ void mma3_shared_b(double (&c)[NT][2], const double (&a)[NT][3], const double (&b)[3], int n_on = NT) {
+#pragma unroll
+  for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+      if (i < n_on) dmma_884(c[i], a[i][kt], b[kt]);
+}
+
 // Store a tile into a row-major matrix C (even stride, even column offset) as one 16-byte store
 // per lane.  Rows >= mc and column pairs starting at >= nc_pad are dropped (nc_pad even; a pad
 // column inside the pair receives an exact zero because the B operand's pad column is zero).
@@ -278,6 +302,12 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   plant_linearize_part_x<S::PLANT>(part, xh, uf, wk + kWAc, kLD, wk + kWXc, kLD, inv, wk + kWCc);
 }
 
+#ifdef CMPC_PHASE_TIMING
+#define CMPC_TICK(i) do { if (threadIdx.x == 0) { G.ticks[size_t(blockIdx.x) * 16 + (i)] = clock64() - tick_t0_; } } while (0)
+#else
+#define CMPC_TICK(i) do { } while (0)
+#endif
+
 // ---- K1: discretisation, prediction and QP assembly of one scenario per CTA --------------------
 template <class S, int RPT>
 __global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
@@ -285,6 +315,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
   constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NCH = S::NCH, NSC = S::NSC, NH = S::NH;
+#ifdef CMPC_PHASE_TIMING
+  const long long tick_t0_ = clock64();
+#endif
   const int scen = blockIdx.x;
   if (scen >= P.batch) return;
   const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
@@ -349,25 +382,25 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   else if (t < 8) dxd[t - 4] = yd_v;
   group_sync(g, TPC);
 
+  CMPC_TICK(0);
   // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) on the FP64 tensor cores -------------
   // every N x N product is 2 x 2 output tiles of 8 x 8 with K = 12 (3 DMMA per tile); warp w of
   // the group owns the row block mt = w, so its A fragments are loaded once per product.
   const int mt_w = warp & 1;
   {
-    double a[3], b0[3], b1[3], c0[2], c1[2];
+    double a[3], bb[3][3], cc[3][2];
     frag_a(Ac, kLD, mt_w, lane, a);
-    frag_b(Ac, kLD, 0, lane, b0);
-    frag_b(Ac, kLD, 1, lane, b1);
-    mma3(c0, a, b0);
-    mma3(c1, a, b1);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1);
+    frag_b(Ac, kLD, 0, lane, bb[0]);
+    frag_b(Ac, kLD, 1, lane, bb[1]);
+    frag_b(Xc, kLD, 0, lane, bb[2]);
+    mma3_shared_a<3>(cc, a, bb, 2);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0]);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1]);
     group_sync(g, TPC);
     frag_a(A2, kLD, mt_w, lane, a);
-    mma3(c0, a, b0);
-    mma3(c1, a, b1);
-    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0);
-    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1);
+    mma3_shared_a<3>(cc, a, bb, 2);
+    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0]);
+    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1]);
     group_sync(g, TPC);
     const double Ts = P.Ts;
     const double k1 = Ts, k2 = Ts * Ts / 2.0, k3 = Ts * Ts * Ts / 6.0, k4 = Ts * Ts * Ts * Ts / 24.0;
@@ -377,15 +410,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     }
     group_sync(g, TPC);
     // Ad = I + Acom Ac (into the A2 slot), [Bd | fd] = Acom Xc
-    double bx[3], cx[2];
     frag_a(Acom, kLD, mt_w, lane, a);
-    frag_b(Xc, kLD, 0, lane, bx);
-    mma3(c0, a, b0);
-    mma3(c1, a, b1);
-    mma3(cx, a, bx);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, c0, true);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, c1, true);
-    tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cx);
+    mma3_shared_a<3>(cc, a, bb, 3);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0], true);
+    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1], true);
+    tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
     group_sync(g, TPC);
   }
   double* Pw = scr + kNNP;  // Ad lives in the A2 slot: Pw[j] = Ad^(2^j) = scr + (1 + j) kNNP
@@ -395,6 +424,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       gl[idx] = (idx < N * N) ? Pw[(idx / N) * kLD + idx % N] : BF[((idx - N * N) / 5) * kNC + (idx - N * N) % 5];
   }
 
+  CMPC_TICK(1);
   // ---- phase 4: powers Ad^(2^j) with baby (L), giant (R) and delay (V) steps by doubling ----
   // L_a = C~ Ad^a (a < 8): rows [2^j, 2^(j+1)) = rows [0, 2^j) * Ad^(2^j), j = 0..2
   // V_a = Ad^a Bd[:, delayed] (a < 8), same doubling on the left
@@ -449,44 +479,61 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
       group_sync(g, TPC);
     }
+    if (j == 3) CMPC_TICK(8);
     // this warp's row block of Pm multiplies: Pm (squaring), V (j < 3), R (j >= 3);
-    // its column block of Pm is multiplied by the rows of L (j < 3)
-    double a[3], b[3], c[2];
+    // its column block of Pm is multiplied by the rows of L (j < 3).  All products of a stage
+    // are independent: their DMMAs are issued interleaved.
+    double a[3], bq[6][3], cq[6][2];   // tiles 0,1: squaring; 2..5: V (j < 3) or column blocks of R
     frag_a(Pm, kLD, mt_w, lane, a);
-    if (s < P.n_pow) {
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        frag_b(Pm, kLD, nt, lane, b);
-        mma3(c, a, b);
-        tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, nt, lane, c);
-      }
-    }
+    const bool do_sq = s < P.n_pow;    // (the last stage squares once more than needed; its result is dropped)
+    frag_b(Pm, kLD, 0, lane, bq[0]);
+    frag_b(Pm, kLD, 1, lane, bq[1]);
     if (j < 3) {
-      const int vc = 2 << j, l_rows = (1 << j) * NY;
-      frag_b(V, kLDV, 0, lane, b);
-      mma3(c, a, b);
-      tile_store(V, kLDV, 0, vc, N, vc, mt_w, 0, lane, c);
-      double al[3];
-      frag_b(Pm, kLD, mt_w, lane, b);      // column block nt = w of Pm
-      for (int mt = 0; mt < ((l_rows + 7) >> 3); ++mt) {
-        frag_a(L, kLD, mt, lane, al);
-        mma3(c, al, b);
-        tile_store(L, kLD, l_rows, 0, l_rows, kLD, mt, mt_w, lane, c);
-      }
+      const int vc = 2 << j, l_rows = (1 << j) * NY, n_lm = (l_rows + 7) >> 3;
+      frag_b(V, kLDV, 0, lane, bq[2]);
+      double al[2][3], bl[3], cl[2][2];
+      frag_b(Pm, kLD, mt_w, lane, bl);      // column block nt = w of Pm
+      frag_a(L, kLD, 0, lane, al[0]);
+      frag_a(L, kLD, 1, lane, al[1]);
+      mma3_shared_a<6>(cq, a, bq, 3);
+      mma3_shared_b<2>(cl, al, bl, n_lm);
+      tile_store(V, kLDV, 0, vc, N, vc, mt_w, 0, lane, cq[2]);
+      tile_store(L, kLD, l_rows, 0, l_rows, kLD, 0, mt_w, lane, cl[0]);
+      if (n_lm > 1) tile_store(L, kLD, l_rows, 0, l_rows, kLD, 1, mt_w, lane, cl[1]);
     } else {
       const int r_base = 1 << (j - 3);
       int cnt = r_base;
       if (r_base + cnt > b_max) cnt = b_max - r_base;
       const int r_cols = cnt > 0 ? cnt * kNC : 0;
-      for (int nt = 0; nt < ((r_cols + 7) >> 3); ++nt) {
-        frag_b(R, ldr, nt, lane, b);
-        mma3(c, a, b);
-        tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt, lane, c);
+      const int n_rt = (r_cols + 7) >> 3;
+      // the first (up to) 4 column blocks of R are interleaved with the squaring
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n_rt) frag_b(R, ldr, i, lane, bq[2 + i]);
+      mma3_shared_a<6>(cq, a, bq, 2 + (n_rt < 4 ? n_rt : 4));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, i, lane, cq[2 + i]);
+      // wider stages (long horizons): remaining column blocks, four at a time
+      for (int nt0 = 4; nt0 < n_rt; nt0 += 4) {
+        double bw[4][3], cw[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (nt0 + i < n_rt) frag_b(R, ldr, nt0 + i, lane, bw[i]);
+        mma3_shared_a<4>(cw, a, bw, n_rt - nt0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt0 + i, lane, cw[i]);
       }
+    }
+    if (do_sq) {
+      tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 0, lane, cq[0]);
+      tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 1, lane, cq[1]);
     }
     group_sync(g, TPC);
   }
 
+  CMPC_TICK(2);
   // ---- phase 5: E[a + 8b][y][c] = (L_a R_b)[y][c]: (8 NY x N) (N x b_max kNC) on the tensor cores ----
   // warp w takes the column blocks nt = w, w + WPC, ...; the NY row blocks of L stay in registers.
   {
@@ -506,11 +553,12 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     };
     if (warp == WPC - 1) {
       // CZ[r][y] = (L_a Z_b)[y] with r + 1 = 8 b + a: the block-state part of Sx x_aug for r < 39
-      double bz[3], cz[2];
+      double bz[3], czz[NY][2];
       frag_b(V, kLDV, 0, lane, bz);
+      mma3_shared_b<NY>(czz, al, bz);
 #pragma unroll
       for (int mt = 0; mt < NY; ++mt) {
-        mma3(cz, al[mt], bz);
+        const double (&cz)[2] = czz[mt];
         const int m = 8 * mt + (lane >> 2), n = 2 * (lane & 3);
         const int a = m / NY, y = m % NY;
 #pragma unroll
@@ -529,8 +577,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         if (nt < n_nt) {
           double b[3];
           frag_b(R, ldr, nt, lane, b);
-#pragma unroll
-          for (int mt = 0; mt < NY; ++mt) mma3(acc[i][mt], al[mt], b);
+          mma3_shared_b<NY>(acc[i], al, b);
         }
       }
       group_sync(g, TPC);   // L, R and the powers are dead: E overwrites them
@@ -544,13 +591,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
     } else {
       for (int nt = warp; nt < n_nt; nt += WPC) {
-        double b[3], c[2];
+        double b[3], c[NY][2];
         frag_b(R, ldr, nt, lane, b);
+        mma3_shared_b<NY>(c, al, b);
 #pragma unroll
-        for (int mt = 0; mt < NY; ++mt) {
-          mma3(c, al[mt], b);
-          store_e(mt, nt, c);
-        }
+        for (int mt = 0; mt < NY; ++mt) store_e(mt, nt, c[mt]);
       }
     }
   }
@@ -560,6 +605,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     for (int idx = t; idx < p * NY * 5; idx += TPC) ge[idx] = E[(idx / 5) * kNC + idx % 5];
   }
 
+  CMPC_TICK(3);
   // ---- phase 6: QP assembly.  Thread t owns prediction rows [t*rpt, (t+1)*rpt). ---------------
   //   G_r[y][c]: c < 4 input columns (delayed ones read 40 rows back), c = 4 the fd column
   //   prefix sums over r by a register scan: local totals -> warp scan -> carry across warps
@@ -608,6 +654,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     for (int c = 0; c < NSC; ++c)
       for (int w = 0; w < warp; ++w) off[c] += carry[w * NSC + c];
   }
+  CMPC_TICK(4);
   // Sx x_aug, delay-line part.  Rows r >= 39 read C~ Ad^(r-39) X40 from the table.  Rows r < 39
   // see a partially drained delay line: with r + 1 = 8 b + a the state is Ad^a Z_b plus the a
   // inputs of the current block, i.e. CZ[r] plus a short convolution (fewer than 8 taps).
@@ -634,6 +681,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
     }
   }
+  CMPC_TICK(5);
   double acc[S::NACC];
 #pragma unroll
   for (int i = 0; i < S::NACC; ++i) acc[i] = 0.0;
@@ -690,6 +738,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
     }
   }
+  CMPC_TICK(6);
   group_sync(g, TPC);  // E is dead: reuse it as the reduction buffer
   {
     constexpr int RS = S::NACC | 1;  // odd stride: conflict-free 64-bit stores
@@ -722,6 +771,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
     }
   }
+  CMPC_TICK(7);
   // [Bd | fd] for the a-priori observer update in K2
   for (int i = t; i < N * kNC; i += TPC) wk[kWBF + i] = BF[i];
 }
