@@ -166,9 +166,8 @@ template <class S>
 int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double* x0,
                        ClosedLoopArrays A, bool reinit, cudaStream_t st) {
   const int B = h->cfg.batch;
-  const int blocks = (B + 63) / 64;
   if (reinit) {
-    cl_start_kernel<S::PLANT><<<blocks, 64, 0, st>>>(B, x0, A, h->d_uinit, h->d_uinitfull);
+    cl_start_kernel<S::PLANT><<<(B + 63) / 64, 64, 0, st>>>(B, x0, A, h->d_uinit, h->d_uinitfull);
     h->launches++;
     CU(cudaGetLastError());
     int rc = launch_init<S>(h, A.x, h->d_uinit, h->d_uinitfull, A.y, st);
@@ -176,14 +175,14 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
     h->initialized = true;
   }
   double t = 0.0;
-  for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;
+  for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;  // the reference driver accumulates t += Ts
   for (int k = first_step; k < first_step + n_steps; ++k) {
     int rc = launch_step<S>(h, A.y, A.u, st);
     if (rc) return rc;
-    cl_advance_kernel<S::PLANT, S::NCTRL><<<blocks, 64, 0, st>>>(B, k, t, h->cfg.Ts, A, h->G.status,
-                                                                 h->G.active, h->G.objective);
+    cl_advance_kernel<S::PLANT, S::NCTRL><<<(2 * B + 63) / 64, 64, 0, st>>>(B, k, t, h->cfg.Ts, A, h->G.status,
+                                                                         h->G.active, h->G.objective);
     h->launches++;
-    t += h->cfg.Ts;  // the reference driver accumulates t += Ts
+    t += h->cfg.Ts;
   }
   CU(cudaGetLastError());
   return CMPC_OK;
@@ -755,9 +754,9 @@ int cmpc_plant_integrate(int device, int plant, int nq, double* x, const double*
   CU(cudaMemcpy(dx, x, n * N * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(du, u, n * NIN * sizeof(double), cudaMemcpyHostToDevice));
   if (plant == 0)
-    plant_integrate_kernel<0><<<(nq + 63) / 64, 64>>>(nq, dx, du, Ts, ds);
+    plant_integrate_kernel<0><<<(nq + 3) / 4, 128>>>(nq, dx, du, Ts, ds);
   else
-    plant_integrate_kernel<1><<<(nq + 63) / 64, 64>>>(nq, dx, du, Ts, ds);
+    plant_integrate_kernel<1><<<(nq + 3) / 4, 128>>>(nq, dx, du, Ts, ds);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(x, dx, n * N * sizeof(double), cudaMemcpyDeviceToHost));

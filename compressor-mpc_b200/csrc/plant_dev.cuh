@@ -98,6 +98,27 @@ __device__ __forceinline__ void compressor_derivative(const double x[5], const d
   dxdt[4] = kTauR * (m_rec_ss - mr);
 }
 
+// Same with the inlet mass flow given (used by the lane-pair integrator).
+__device__ __forceinline__ void compressor_derivative_core(const double x[5], const double u[4], double m_in,
+                                                           double p_out, double dxdt[5], double* m_out) {
+  const double p1 = x[0], p2 = x[1], mc = x[2], wc = x[3], mr = x[4];
+  const double td = u[0] * kTorqueDriveC / wc;
+  *m_out = valve_mass_flow<ValveD>(p2, p_out, u[2], kMoutC);
+  const double m_rec_ss =
+      (u[3] > 1e-2) ? (kMrec0 * (sqrt(p2 * 1e5 - p1 * 1e5) * u[3]) + kMrec1) : 0.0;
+  const double mc2 = mc * mc, mc3 = mc * mc2, wc2 = wc * wc;
+  const double q2 = map_a(0) * mc3 + map_a(1) * mc2 + map_a(2) * mc + map_a(3);
+  const double q1 = map_a(4) * mc3 + map_a(5) * mc2 + map_a(6) * mc + map_a(7);
+  const double q0 = map_a(8) * mc3 + map_a(9) * mc2 + map_a(10) * mc + map_a(11);
+  const double p_ratio = wc2 * q2 + wc * q1 + q0;
+  const double T_ss = kTss0 + kTss1 * mc + kTss2;
+  dxdt[0] = (340.0 * 340.0) / kV1 * (m_in + mr - mc) * 1e-5;
+  dxdt[1] = (340.0 * 340.0) / kV2 * (mc - mr - *m_out) * 1e-5;
+  dxdt[2] = kAdivL * (p_ratio * p1 - p2) * 1e5;
+  dxdt[3] = (td - T_ss) / kJ;
+  dxdt[4] = kTauR * (m_rec_ss - mr);
+}
+
 // compressor.cc:68-78
 __device__ __forceinline__ void compressor_output(const double x[5], double* p2_out, double* sd_out) {
   *p2_out = x[1];
@@ -323,6 +344,42 @@ __device__ void plant_linearize_part_x(int part, const double* x, const double* 
     C[3 * N + 10] = 1;
     const double m_out_tank = valve_mass_flow<ValveD>(x[10], 1.0, u[8], kMoutC);
     X[10 * ldx + 4] = (340.0 * 340.0) / kTankVolume * (m_total - m_out_tank) * 1e-5;
+  }
+}
+
+// ---- lane-pair form of the plant ODE --------------------------------------------------------
+// Two neighbouring lanes (parity c = lane & 1) integrate one scenario: lane parity c holds
+// compressor c's five states in xs[0..4]; for the parallel plant both also hold the tank pressure
+// in xs[5] and compute its (identical) derivative.  uc = that compressor's four inputs, u_tank =
+// tank valve (parallel plant).  `full` is the shuffle mask: the two lanes of the pair (pairs of
+// one warp may diverge in the adaptive step loop), or the whole warp when all lanes run in step.
+template <int PLANT>
+__device__ __forceinline__ void pair_derivative(unsigned full, int c, const double xs[6], const double uc[4],
+                                                double u_tank, double d[6]) {
+  if (PLANT == 0) {
+    const double m_in = valve_mass_flow<ValveC>(1.0, xs[0], uc[1], kMinC);
+    double m_out;
+    compressor_derivative_core(xs, uc, m_in, xs[5], d, &m_out);
+    const double m_other = __shfl_xor_sync(full, m_out, 1);
+    const double m0 = c == 0 ? m_out : m_other, m1 = c == 0 ? m_other : m_out;
+    const double m_out_tank = valve_mass_flow<ValveD>(xs[5], 1.0, u_tank, kMoutC);
+    d[5] = (340.0 * 340.0) / kTankVolume * ((m0 + m1) - m_out_tank) * 1e-5;
+  } else {
+    // serial: compressor 0 discharges into compressor 1's inlet volume
+    const double o_p1 = __shfl_xor_sync(full, xs[0], 1);   // the other compressor's p1
+    const double o_p2 = __shfl_xor_sync(full, xs[1], 1);   // the other compressor's p2
+    const double o_uout = __shfl_xor_sync(full, uc[2], 1); // the other compressor's outlet valve
+    double m_in, p_out;
+    if (c == 0) {
+      m_in = valve_mass_flow<ValveC>(1.0, xs[0], uc[1], kMinC);
+      p_out = o_p1;
+    } else {
+      m_in = valve_mass_flow<ValveD>(o_p2, xs[0], o_uout, kMoutC);   // first compressor's outflow
+      p_out = 1.0;
+    }
+    double m_out;
+    compressor_derivative_core(xs, uc, m_in, p_out, d, &m_out);
+    d[5] = 0.0;
   }
 }
 

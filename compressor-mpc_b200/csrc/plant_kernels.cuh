@@ -92,6 +92,101 @@ __device__ int integrate_interval(const double* u, double* x, double Ts) {
   return steps;
 }
 
+// ---- lane-pair Dormand-Prince (same arithmetic per state as dopri5_try_step, same order of the
+// error-norm sum, so step acceptance is bit-identical to the one-thread form) --------------------
+template <int PLANT>
+__device__ bool dopri5_try_step_pair(unsigned full, int c, const double uc[4], double u_tank, double xs[6],
+                                     double k1[6], double* t, double* dt) {
+  constexpr int NS = PLANT == 0 ? 6 : 5;
+  constexpr double b21 = 1.0 / 5;
+  constexpr double b31 = 3.0 / 40, b32 = 9.0 / 40;
+  constexpr double b41 = 44.0 / 45, b42 = -56.0 / 15, b43 = 32.0 / 9;
+  constexpr double b51 = 19372.0 / 6561, b52 = -25360.0 / 2187, b53 = 64448.0 / 6561, b54 = -212.0 / 729;
+  constexpr double b61 = 9017.0 / 3168, b62 = -355.0 / 33, b63 = 46732.0 / 5247, b64 = 49.0 / 176,
+                   b65 = -5103.0 / 18656;
+  constexpr double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+  constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                   dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+  const double h = *dt;
+  double k2[6], k3[6], k4[6], k5[6], k6[6], k7[6], xt[6], xn[6];
+  xt[5] = xn[5] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * b21 * k1[i];
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k2);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b31 * k1[i] + b32 * k2[i]);
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k3);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b41 * k1[i] + b42 * k2[i] + b43 * k3[i]);
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k4);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b51 * k1[i] + b52 * k2[i] + b53 * k3[i] + b54 * k4[i]);
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k5);
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+    xt[i] = xs[i] + h * (b61 * k1[i] + b62 * k2[i] + b63 * k3[i] + b64 * k4[i] + b65 * k5[i]);
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k6);
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+    xn[i] = xs[i] + h * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
+  pair_derivative<PLANT>(full, c, xn, uc, u_tank, k7);
+  // squared scaled errors of this lane's states; summed in plant state order 0..N-1
+  double e2[6];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const double xerr = h * (dc1 * k1[i] + dc3 * k3[i] + dc4 * k4[i] + dc5 * k5[i] + dc6 * k6[i] + dc7 * k7[i]);
+    const double e = fabs(xerr) / (1e-6 + 1e-6 * (fabs(xs[i]) + fabs(h) * fabs(k1[i])));
+    e2[i] = e * e;
+  }
+  double sumsq = 0.0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {   // compressor 0's states
+    const double o = __shfl_xor_sync(full, e2[i], 1);
+    sumsq += (c == 0) ? e2[i] : o;
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {   // compressor 1's states
+    const double o = __shfl_xor_sync(full, e2[i], 1);
+    sumsq += (c == 1) ? e2[i] : o;
+  }
+  if (PLANT == 0) sumsq += e2[5];
+  double err = sqrt(sumsq);
+  if (err > 1.0) {
+    *dt = h * fmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
+    return false;
+  }
+  *t += h;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    xs[i] = xn[i];
+    k1[i] = k7[i];
+  }
+  if (err < 0.5) {
+    err = fmax(1.0 / 3125.0, err);
+    *dt = h * 9.0 / 10.0 * pow(err, -1.0 / 5.0);
+  }
+  return true;
+}
+
+template <int PLANT>
+__device__ int integrate_interval_pair(unsigned full, int c, const double uc[4], double u_tank, double xs[6],
+                                       double Ts) {
+  double k1[6];
+  pair_derivative<PLANT>(full, c, xs, uc, u_tank, k1);
+  double t = 0.0, dt = Ts;
+  int steps = 0, fails = 0;
+  const double eps = 2.220446049250313e-16;
+  while (Ts - t > eps) {
+    if ((t + dt) - Ts > eps) dt = Ts - t;
+    while (!dopri5_try_step_pair<PLANT>(full, c, uc, u_tank, xs, k1, &t, &dt)) {
+      if (++fails > 500) return -1;
+    }
+    fails = 0;
+    ++steps;
+  }
+  return steps;
+}
+
 struct ClosedLoopArrays {
   double* x;           // [B][N] plant state
   double* y;           // [B][4] measurement handed to the controller
@@ -130,50 +225,81 @@ __global__ void cl_start_kernel(int B, const double* __restrict__ x0, ClosedLoop
   for (int i = 0; i < NIN; ++i) u_init_full[size_t(b) * NIN + i] = PLANT == 0 ? udef_par[i] : udef_ser[i];
 }
 
-// After the control step of record k: write the record, push u through the delay rings,
-// integrate the plant over one sampling interval and produce the next measurement.
+// ---- plant side of the closed loop: one lane pair per scenario (16 scenarios per warp) ---------
+// After the control step of record k: write the record, push u through the
+// actuator delay rings, integrate the plant over one sampling interval (one compressor per lane
+// of the pair) and produce the next measurement.
 template <int PLANT, int NCTRL>
-__global__ void cl_advance_kernel(int B, int k, double t_k, double Ts, ClosedLoopArrays A,
-                                  const int* __restrict__ status, const unsigned* __restrict__ active,
-                                  const double* __restrict__ objective) {
+__global__ void __launch_bounds__(64)
+cl_advance_kernel(int B, int k, double t_k, double Ts, ClosedLoopArrays A, const int* __restrict__ status,
+                  const unsigned* __restrict__ active, const double* __restrict__ objective) {
   constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN, REC = 1 + N + 8;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = tid >> 1, c = tid & 1;
   if (b >= B) return;
-  double x[N], u[4], up[NIN];
-  for (int i = 0; i < N; ++i) x[i] = A.x[size_t(b) * N + i];
+  const unsigned pair_mask = 3u << (threadIdx.x & 30);
+  double u[4];
+#pragma unroll
   for (int i = 0; i < 4; ++i) u[i] = A.u[size_t(b) * 4 + i];
+  double xs[6];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) xs[i] = A.x[size_t(b) * N + 5 * c + i];
+  xs[5] = PLANT == 0 ? A.x[size_t(b) * N + (PLANT == 0 ? 10 : 0)] : 0.0;
   if (A.traj) {
     double* r = A.traj + (size_t(b) * A.n_steps + k) * REC;
-    r[0] = t_k;
-    for (int i = 0; i < N; ++i) r[1 + i] = x[i];
-    for (int i = 0; i < 4; ++i) r[1 + N + i] = u[i];
-    for (int i = 0; i < 4; ++i) r[1 + N + 4 + i] = A.y[size_t(b) * 4 + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) r[1 + 5 * c + i] = xs[i];
+    if (c == 0) {
+      r[0] = t_k;
+      if (PLANT == 0) r[1 + (PLANT == 0 ? 10 : 0)] = xs[5];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[1 + N + i] = u[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[1 + N + 4 + i] = A.y[size_t(b) * 4 + i];
+    }
   }
-  for (int c = 0; c < NCTRL; ++c) {
+  if (c < NCTRL) {
     const size_t o = (size_t(b) * A.n_steps + k) * NCTRL + c;
     if (A.qp_active) A.qp_active[o] = active[b * NCTRL + c];
     if (A.qp_objective) A.qp_objective[o] = objective[b * NCTRL + c];
     if (A.qp_status) A.qp_status[o] = status[b * NCTRL + c];
   }
-  // plant-input offsets of the block this record belongs to (SetOffset)
+  // plant-input offsets of the block this record belongs to (SetOffset); TimeDelay: this
+  // compressor's recycle valve command (control input 2c+1) comes out 40 samples late
   int blk = 0;
   while (blk + 1 < A.n_blocks && k >= A.block_end[b * A.n_blocks + blk]) ++blk;
+  const int pos = k % kDelay;
+  double* ring = A.ring + (size_t(b) * 2 + c) * kDelay;
+  const double ud = ring[pos];
+  ring[pos] = u[2 * c + 1];
   constexpr double udef_par[9] = {0.304, 0.43, 1.0, 0, 0.304, 0.43, 1.0, 0, 0.7};
   constexpr double udef_ser[8] = {0.304, 0.405, 1, 0, 0.304, -1, 0.393, 0};
-  for (int i = 0; i < NIN; ++i)
-    up[i] = (PLANT == 0 ? udef_par[i] : udef_ser[i]) + A.block_off[(size_t(b) * A.n_blocks + blk) * NIN + i];
-  // TimeDelay: inputs 1 and 3 come out 40 samples late
-  const int pos = k % kDelay;
-  double* ring = A.ring + size_t(b) * 2 * kDelay;
-  double ud[4] = {u[0], ring[pos], u[2], ring[kDelay + pos]};
-  ring[pos] = u[1];
-  ring[kDelay + pos] = u[3];
-  up[0] += ud[0]; up[3] += ud[1]; up[4] += ud[2]; up[7] += ud[3];
-  integrate_interval<PLANT>(up, x, Ts);
-  double y[4];
-  plant_output<PLANT>(x, y);
-  for (int i = 0; i < N; ++i) A.x[size_t(b) * N + i] = x[i];
-  for (int i = 0; i < 4; ++i) A.y[size_t(b) * 4 + i] = y[i];
+  const double* off = A.block_off + (size_t(b) * A.n_blocks + blk) * NIN;
+  double uc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) uc[i] = (PLANT == 0 ? udef_par[4 * c + i] : udef_ser[4 * c + i]) + off[4 * c + i];
+  uc[0] += u[2 * c];
+  uc[3] += ud;
+  const double u_tank = PLANT == 0 ? udef_par[8] + off[PLANT == 0 ? 8 : 0] : 0.0;
+  integrate_interval_pair<PLANT>(pair_mask, c, uc, u_tank, xs, Ts);
+  // next measurement: the other compressor's pressures and flow come by shuffle
+  double p2, sd;
+  compressor_output(xs, &p2, &sd);
+  const double p2_o = __shfl_xor_sync(pair_mask, p2, 1), sd_o = __shfl_xor_sync(pair_mask, sd, 1);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) A.x[size_t(b) * N + 5 * c + i] = xs[i];
+  if (c == 0) {
+    double y[4];
+    if (PLANT == 0) {
+      y[0] = sd; y[1] = sd_o; y[2] = p2 - p2_o; y[3] = xs[5];
+      A.x[size_t(b) * N + (PLANT == 0 ? 10 : 0)] = xs[5];
+    } else {
+      y[0] = p2; y[1] = sd; y[2] = p2_o; y[3] = sd_o;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) A.y[size_t(b) * 4 + i] = y[i];
+  }
 }
 
 // NerveCenter::Initialize + DistributedController::Initialize (nerve_center.h:98-104,186-203,
@@ -221,18 +347,24 @@ __global__ void plant_eval_kernel(int nq, const double* __restrict__ x, const do
   if (C) for (int i = 0; i < 4 * N; ++i) C[size_t(b) * 4 * N + i] = Cl[i];
 }
 
+// One warp per entry; the lane pairs of the warp all integrate the same scenario.
 template <int PLANT>
 __global__ void plant_integrate_kernel(int nq, double* x, const double* __restrict__ u, double Ts,
                                        int* n_substeps) {
   constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ln = threadIdx.x & 31, c = ln & 1;
   if (b >= nq) return;
-  double xl[N], ul[NIN];
-  for (int i = 0; i < N; ++i) xl[i] = x[size_t(b) * N + i];
-  for (int i = 0; i < NIN; ++i) ul[i] = u[size_t(b) * NIN + i];
-  const int s = integrate_interval<PLANT>(ul, xl, Ts);
-  for (int i = 0; i < N; ++i) x[size_t(b) * N + i] = xl[i];
-  if (n_substeps) n_substeps[b] = s;
+  double xs[6], uc[4];
+  for (int i = 0; i < 5; ++i) xs[i] = x[size_t(b) * N + 5 * c + i];
+  xs[5] = PLANT == 0 ? x[size_t(b) * N + 10] : 0.0;
+  for (int i = 0; i < 4; ++i) uc[i] = u[size_t(b) * NIN + 4 * c + i];
+  const double u_tank = PLANT == 0 ? u[size_t(b) * NIN + 8] : 0.0;
+  const int s = integrate_interval_pair<PLANT>(0xffffffffu, c, uc, u_tank, xs, Ts);
+  if (ln < 2) {
+    for (int i = 0; i < 5; ++i) x[size_t(b) * N + 5 * c + i] = xs[i];
+    if (PLANT == 0 && ln == 0) x[size_t(b) * N + 10] = xs[5];
+  }
+  if (n_substeps && ln == 0) n_substeps[b] = s;
 }
 
 template <int NV>

@@ -253,26 +253,20 @@ __device__ __forceinline__ double plant_c_row_dot(const double* x, int r, const 
 // controller): each repeats the tiny observer update in registers, three of them fill one part
 // of the continuous-time matrices in the hand-over record (whose zero pattern never changes).
 template <class S>
-__global__ void __launch_bounds__(128)
-lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
+__device__ __forceinline__ void lin_part(const StepParams& P, const DeviceState& G, int scen, int g, int part,
+                                         const double (&yv)[4]) {
   constexpr int N = S::N, NOBS = S::NOBS, NIN = S::NIN;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int part = tid & 3, quad = tid >> 2;
-  const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
-  if (scen >= P.batch) return;
   double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   const double* ss = G.scen + size_t(scen) * kScenStateStride;
   double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
-  double xh[N], dx[NOBS], ev[4], yv[4];
+  double xh[N], dx[NOBS], ev[4];
 #pragma unroll
   for (int i = 0; i < N; ++i) xh[i] = gs[kOffXhat + i];
 #pragma unroll
   for (int i = 0; i < NOBS; ++i) dx[i] = gs[kOffDx + i];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    yv[r] = y[size_t(scen) * 4 + r];
+  for (int r = 0; r < 4; ++r)
     ev[r] = yv[r] - gs[kOffYold + r] - (plant_c_row_dot<S::PLANT>(xh, r, dx) + dx[N + r]);
-  }
 #pragma unroll
   for (int i = 0; i < NOBS; ++i) {
     double acc = dx[i];
@@ -300,6 +294,19 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) inv[P.c[g].ctrl_idx[c]] = c;
   plant_linearize_part_x<S::PLANT>(part, xh, uf, wk + kWAc, kLD, wk + kWXc, kLD, inv, wk + kWCc);
+}
+
+template <class S>
+__global__ void __launch_bounds__(128)
+lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int part = tid & 3, quad = tid >> 2;
+  const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
+  if (scen >= P.batch) return;
+  double yv[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) yv[r] = y[size_t(scen) * 4 + r];
+  lin_part<S>(P, G, scen, g, part, yv);
 }
 
 #ifdef CMPC_PHASE_TIMING
@@ -797,6 +804,10 @@ __device__ __noinline__ int qp_fallback4(const double* H, double f0, double f1, 
   return st;
 }
 
+__device__ __forceinline__ double sel4(const double (&a)[4], int i) {
+  return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3];
+}
+
 // ---- K2: Jacobi sweeps (nerve_center.h:146-158,275-296), first move (nerve_center.h:162-167,
 // 313-319), UpdateU / ObserveAPriori (distributed_controller.h:146-152, observer.cc:6-19).
 // One warp per scenario.
@@ -804,13 +815,10 @@ __device__ __noinline__ int qp_fallback4(const double* H, double f0, double f1, 
 #define CMPC_SOLVE_MIN_BLOCKS 3
 #endif
 template <class S>
-__global__ void __launch_bounds__(128, S::NV == 4 ? CMPC_SOLVE_MIN_BLOCKS : 2)
-solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+__device__ __forceinline__ void solve_and_update(const StepParams& P, const DeviceState& G, int scen, int ln,
+                                                 double (&u_new)[4]) {
   constexpr int N = S::N, NU = S::NU, NV = S::NV, NVO = S::NVO, NTOT = S::NTOT, NOBS = S::NOBS;
   constexpr int NCTRL = S::NCTRL;
-  const int ln = threadIdx.x & 31;
-  const int scen = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (scen >= P.batch) return;
   double* ss = G.scen + size_t(scen) * kScenStateStride;
   const size_t sc0 = size_t(scen) * NCTRL;
   // first moves of every controller, system input order (valid on all lanes after the sweeps)
@@ -959,11 +967,10 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
   }
 
   // nerve_center.h:162-167,313-319: u_old_ += first move of each controller's plan
-  if (ln < 4) {
-    const double un = ss[ln] + du_sys[ln];
-    u[size_t(scen) * 4 + ln] = un;
-    ss[ln] = un;
-  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) u_new[k] = ss[k] + du_sys[k];
+  __syncwarp();
+  if (ln < 4) ss[ln] = sel4(u_new, ln);
   // UpdateU / ObserveAPriori for every controller: each sees only its own inputs move
   // (nerve_center.h:322-328); lanes split the augmented state
   for (int c = 0; c < NCTRL; ++c) {
@@ -971,7 +978,7 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     const double* BF = G.work + (sc0 + c) * kWorkStride + kWBF;
     double du[4] = {0.0, 0.0, 0.0, 0.0}, uold[4];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) du[i] = du_sys[c * NU + i];
+    for (int i = 0; i < NU; ++i) du[i] = sel4(du_sys, c * NU + i);
 #pragma unroll
     for (int i = 0; i < 4; ++i) uold[i] = gs[kOffUold + i];
     const double h0 = gs[kOffDx + NOBS + 0] - uold[1], h1 = gs[kOffDx + NOBS + 1] - uold[3];
@@ -1002,6 +1009,17 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     }
     if (ln < 4) gs[kOffUold + ln] = uold[ln] + du[ln];
   }
+}
+
+template <class S>
+__global__ void __launch_bounds__(128, S::NV == 4 ? CMPC_SOLVE_MIN_BLOCKS : 2)
+solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+  const int ln = threadIdx.x & 31;
+  const int scen = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (scen >= P.batch) return;
+  double u_new[4];
+  solve_and_update<S>(P, G, scen, ln, u_new);
+  if (ln < 4) u[size_t(scen) * 4 + ln] = sel4(u_new, ln);
 }
 
 }  // namespace cmpc
