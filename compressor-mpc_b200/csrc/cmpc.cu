@@ -124,6 +124,7 @@ template <class S>
 int launch_init(cmpc_handle* h, const double* x, const double* u, const double* uf, const double* y,
                 cudaStream_t st) {
   const int B = h->cfg.batch;
+  h->P.ring_pos = 0;
   init_kernel<S><<<(B + 127) / 128, 128, 0, st>>>(B, h->G, x, u, uf, y, h->P);
   h->launches++;
   CU(cudaGetLastError());
@@ -155,7 +156,8 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
     assemble_kernel<S, 4><<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
   if (ev) CU(cudaEventRecord(ev[2], st));
   // K2: Jacobi sweeps + update; one warp per scenario
-  solve_kernel<S><<<(B + 3) / 4, 128, 0, st>>>(h->P, h->G, u);
+  solve_kernel<S><<<(B * S::NCTRL + 63) / 64, 64, 0, st>>>(h->P, h->G, u);
+  h->P.ring_pos = (h->P.ring_pos + 1) % kRing;   // the oldest ring slot was consumed and refilled
   if (ev) CU(cudaEventRecord(ev[3], st));
   h->launches += 3;
   CU(cudaGetLastError());
@@ -674,7 +676,14 @@ int cmpc_get_controller_state(cmpc_handle* h, int ctrl, double* x_hat, double* d
   for (size_t b = 0; b < B; ++b) {
     const double* r = buf.data() + (b * h->NCTRL + ctrl) * kCtrlStateStride;
     if (x_hat) std::memcpy(x_hat + b * N, r + kOffXhat, sizeof(double) * N);
-    if (dx_aug) std::memcpy(dx_aug + b * NT, r + kOffDx, sizeof(double) * NT);
+    if (dx_aug) {
+      // logical order: [x | d | heads | chain 0 | chain 1]; the chains are rings starting at ring_pos
+      std::memcpy(dx_aug + b * NT, r + kOffDx, sizeof(double) * (N + kNDist + 2));
+      for (int d = 0; d < 2; ++d)
+        for (int j = 0; j < kRing; ++j)
+          dx_aug[b * NT + N + kNDist + 2 + d * kRing + j] =
+              r[kOffDx + N + kNDist + 2 + d * kRing + (h->P.ring_pos + j) % kRing];
+    }
     if (y_old) std::memcpy(y_old + b * 4, r + kOffYold, sizeof(double) * 4);
     if (u_old) std::memcpy(u_old + b * 4, r + kOffUold, sizeof(double) * 4);
   }

@@ -34,7 +34,7 @@
 
 #include "plant_dev.cuh"
 #include "qp_dev.cuh"
-#include "qp_warp.cuh"
+#include "qp_thread.cuh"
 
 namespace cmpc {
 
@@ -52,6 +52,9 @@ constexpr int kScenStateStride = 16;   // doubles per scenario
 // hand-over record of one (scenario, controller): continuous A (12 x 12, zero padded),
 // [Bc | fc] in the controller's input order (12 x 12, zero padded), C (4 x N), [Bd | fd] (N x 6)
 constexpr int kWorkStride = 512, kWAc = 0, kWXc = 144, kWCc = 288, kWBF = 336;
+// kWBF holds what the a-priori observer update needs: base[N] (free response of the state part),
+// then the Bd columns of the undelayed inputs 0 and 2 (N each)
+constexpr int kRing = kDelay - 1;   // slots of one delay ring (the head is kept separately)
 constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
 
 // offsets inside one controller's global state record
@@ -82,6 +85,7 @@ struct CtrlParams {
 
 struct StepParams {
   int p, b_max, n_pow, n_iter, batch, ldr;
+  int ring_pos;   // position of the oldest entry in the 39-slot delay rings (same for all scenarios)
   double Ts;
   const double* yref;   // [NCTRL][p][NY]
   CtrlParams c[2];
@@ -362,7 +366,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     q_v[k] = 0.0;
     if (i < 2 * kDelay) {
       const int d = i / kDelay, tt = i % kDelay;
-      const int slot = (tt == 0) ? (NOBS + d) : (NOBS + 2 + d * (kDelay - 1) + tt - 1);
+      // head, then the ring in logical order (oldest first)
+      const int slot = (tt == 0) ? (NOBS + d) : (NOBS + 2 + d * kRing + (P.ring_pos + tt - 1) % kRing);
       q_v[k] = gs[kOffDx + slot] - gs[kOffUold + 1 + 2 * d];
     }
   }
@@ -779,8 +784,14 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     }
   }
   CMPC_TICK(7);
-  // [Bd | fd] for the a-priori observer update in K2
-  for (int i = t; i < N * kNC; i += TPC) wk[kWBF + i] = BF[i];
+  // what the a-priori observer update (observer.cc:6-19) needs in K2: the part of the new
+  // state estimate that does not depend on the move, B (head - u_old) + f_d, and the Bd columns
+  // of the undelayed inputs
+  if (t < N) {
+    wk[kWBF + t] = fma(BF[t * kNC + 1], q[0], fma(BF[t * kNC + 3], q[kDelay], BF[t * kNC + 4]));
+    wk[kWBF + N + t] = BF[t * kNC + 0];
+    wk[kWBF + 2 * N + t] = BF[t * kNC + 2];
+  }
 }
 
 // General solve for one 4-variable QP when the warm-start working set is no longer optimal.
@@ -804,222 +815,202 @@ __device__ __noinline__ int qp_fallback4(const double* H, double f0, double f1, 
   return st;
 }
 
-__device__ __forceinline__ double sel4(const double (&a)[4], int i) {
-  return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3];
+// UpdateU / ObserveAPriori of one controller (distributed_controller.h:146-152, observer.cc:6-19),
+// one thread: new state part = base + Bd[:,0] du0 (+ Bd[:,2] du2), the disturbance estimate stays,
+// each delay line hands its oldest entry to the head and takes the newly commanded input
+// (the chains are rings: position P.ring_pos is the oldest slot and becomes the newest).
+template <class S>
+__device__ __forceinline__ void apriori_update(const StepParams& P, const DeviceState& G, size_t ctrl_rec,
+                                               const double (&du)[4]) {
+  constexpr int N = S::N, NOBS = S::NOBS;
+  double* gs = G.ctrl + ctrl_rec * kCtrlStateStride;
+  const double* wb = G.work + ctrl_rec * kWorkStride + kWBF;
+  double base[N], c0[N], c2[N], uold[4];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { base[i] = wb[i]; c0[i] = wb[N + i]; c2[i] = wb[2 * N + i]; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) uold[i] = gs[kOffUold + i];
+  const int ring0 = kOffDx + NOBS + 2 + P.ring_pos, ring1 = ring0 + kRing;
+  const double old0 = gs[ring0], old1 = gs[ring1];
+#pragma unroll
+  for (int i = 0; i < N; ++i) gs[kOffDx + i] = fma(c0[i], du[0], fma(c2[i], du[2], base[i]));
+  gs[kOffDx + NOBS + 0] = old0;
+  gs[kOffDx + NOBS + 1] = old1;
+  gs[ring0] = uold[1] + du[1];
+  gs[ring1] = uold[3] + du[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) gs[kOffUold + i] = uold[i] + du[i];
 }
 
 // ---- K2: Jacobi sweeps (nerve_center.h:146-158,275-296), first move (nerve_center.h:162-167,
-// 313-319), UpdateU / ObserveAPriori (distributed_controller.h:146-152, observer.cc:6-19).
-// One warp per scenario.
+// 313-319), UpdateU / ObserveAPriori.  Distributed controllers: one thread per sub-controller,
+// the pair of a scenario in neighbouring lanes (16 scenarios per warp).  Centralised: one thread
+// per scenario with the general solver.
 #ifndef CMPC_SOLVE_MIN_BLOCKS
-#define CMPC_SOLVE_MIN_BLOCKS 3
+#define CMPC_SOLVE_MIN_BLOCKS 1
 #endif
 template <class S>
-__device__ __forceinline__ void solve_and_update(const StepParams& P, const DeviceState& G, int scen, int ln,
-                                                 double (&u_new)[4]) {
-  constexpr int N = S::N, NU = S::NU, NV = S::NV, NVO = S::NVO, NTOT = S::NTOT, NOBS = S::NOBS;
-  constexpr int NCTRL = S::NCTRL;
-  double* ss = G.scen + size_t(scen) * kScenStateStride;
-  const size_t sc0 = size_t(scen) * NCTRL;
-  // first moves of every controller, system input order (valid on all lanes after the sweeps)
-  double du_sys[4] = {0.0, 0.0, 0.0, 0.0};
-
+__global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
+solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+  constexpr int NU = S::NU, NV = S::NV, NVO = S::NVO, NCTRL = S::NCTRL;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (NV == 4 && NCTRL == 2) {
-    // 16 lanes per sub-controller, everything in registers (qp_warp.cuh)
-    QpLane QL;
-    QL.half = ln >> 4; QL.i = (ln >> 2) & 3; QL.j = ln & 3; QL.base = ln & 16;
-    const int c = QL.half;
-    const double* gH = G.qpH + (sc0 + c) * NV * NV;
-    const double* gf = G.qpf + (sc0 + c) * NV;
-    const double* gG = G.qpG + (sc0 + c) * NV * NVO;
-    const double* uo = G.ctrl + (sc0 + c) * kCtrlStateStride + kOffUold;
-    unsigned wset = G.guess[sc0 + c];
-    const double Hij = gH[QL.i * 4 + QL.j];
-    const double Gij = gG[QL.i * 4 + QL.j];
-    const double f0 = gf[QL.i];
-    double z_col = ss[4 + c * NV + QL.j];      // du_prev = du_old_ (own plan, entry j)
-    // right-hand side of this lane's own constraint (kind = i, variable = j), a'z >= b form
-    double bnd;
-    {
-      const int iu = QL.j & 1;
-      const double uold = uo[iu];
-      const double lo = P.c[c].lower[iu] - uold, up = P.c[c].upper[iu] - uold;
-      bnd = (QL.i == 0) ? lo : (QL.i == 1) ? -up : (QL.i == 2) ? P.c[c].rate_lower[iu] : -P.c[c].rate_upper[iu];
+    const int scen = tid >> 1, c = tid & 1;
+    if (scen >= P.batch) return;
+    const unsigned pm = 3u << (threadIdx.x & 30);   // the two lanes of this scenario
+    double* ss = G.scen + size_t(scen) * kScenStateStride;
+    const size_t rec = size_t(scen) * 2 + c;
+    const double* gH = G.qpH + rec * 16;
+    const double* gf = G.qpf + rec * 4;
+    const double* gG = G.qpG + rec * 16;
+    const double* uo = G.ctrl + rec * kCtrlStateStride + kOffUold;
+    double J[4][4], Hm[4][4], Gx[4][4], f0[4], z[4], bnd[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f0[i] = gf[i];
+      z[i] = ss[4 + c * 4 + i];          // du_prev = du_old_ (own plan)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Hm[i][j] = gH[i * 4 + j];
+        J[i][j] = Hm[i][j];
+        Gx[i][j] = gG[i * 4 + j];
+      }
     }
-    bool pd;
-    const double J = qw_inverse(Hij, QL, &pd);
-    if (wset == kQpNoGuess) wset = 0;          // no warm start: begin from the unconstrained minimiser
-    QpReduced red;
-    bool red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
-    double x_row = 0.0, lam_row = 0.0, f_row = f0;
+    const double uo0 = uo[0], uo1 = uo[1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double uold = (i & 1) ? uo1 : uo0;
+      bnd[i] = P.c[c].lower[i & 1] - uold;
+      bnd[4 + i] = -(P.c[c].upper[i & 1] - uold);
+      bnd[8 + i] = P.c[c].rate_lower[i & 1];
+      bnd[12 + i] = -P.c[c].rate_upper[i & 1];
+    }
+    unsigned wset = G.guess[rec];
+    if (wset == kQpNoGuess) wset = 0;     // no warm start: begin from the unconstrained minimiser
+    const bool pd = qt_inverse(J);
+    QtReduced red;
+    bool red_ok = qt_prepare(J, bnd, wset, red) && pd;
+    double x[4] = {0.0, 0.0, 0.0, 0.0}, lam[4] = {0.0, 0.0, 0.0, 0.0}, fi[4] = {0.0, 0.0, 0.0, 0.0};
     int status = pd ? 0 : 3;
     for (int it = 0; it < P.n_iter; ++it) {
-      const double zo = __shfl_xor_sync(kFullMask, z_col, 16);   // the other controller's previous plan
-      f_row = f0 + qw_row_sum(Gij * zo);
-      bool ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
-      const bool need_slow = pd && !ok;
-      if (__any_sync(kFullMask, need_slow)) {
-        // the working set changes (rare): lane 0 of the half runs the general dual active-set
-        // solver, the half rebuilds its reduced system for the new set
-        double fi[4];
+      double zo[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) fi[k] = qw_get(f_row, QL, k, 0);
+      for (int k = 0; k < 4; ++k) zo[k] = __shfl_xor_sync(pm, z[k], 1);   // the other controller's previous plan
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double s = f0[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = fma(Gx[i][k], zo[k], s);
+        fi[i] = s;
+      }
+      bool ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
+      // the working set changes: repair it one constraint at a time in registers (each accepted
+      // result satisfies the KKT conditions of the full QP, i.e. is the unique minimiser) ...
+      for (int rep = 0; rep < 6 && pd && !ok && red_ok; ++rep) {
+        const unsigned nw = qt_repair(red, x, lam, bnd, wset);
+        if (nw == wset) break;
+        wset = nw;
+        red_ok = qt_prepare(J, bnd, wset, red);
+        ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
+      }
+      if (pd && !ok) {
+        // ... and only if that does not settle, the general dual active-set solve
+        QpBounds4 qb;
+        qb.lo0 = bnd[0]; qb.lo1 = bnd[1]; qb.up0 = -bnd[4]; qb.up1 = -bnd[5];
+        qb.rlo0 = bnd[8]; qb.rlo1 = bnd[9]; qb.rup0 = -bnd[12]; qb.rup1 = -bnd[13];
         unsigned new_w = wset;
-        int st = 0;
-        if (need_slow && ln == QL.base) {
-          QpBounds4 qb;
-          qb.lo0 = P.c[c].lower[0] - uo[0]; qb.lo1 = P.c[c].lower[1] - uo[1];
-          qb.up0 = P.c[c].upper[0] - uo[0]; qb.up1 = P.c[c].upper[1] - uo[1];
-          qb.rlo0 = P.c[c].rate_lower[0]; qb.rlo1 = P.c[c].rate_lower[1];
-          qb.rup0 = P.c[c].rate_upper[0]; qb.rup1 = P.c[c].rate_upper[1];
-          st = qp_fallback4(gH, fi[0], fi[1], fi[2], fi[3], qb, &new_w);
-        }
-        st = __shfl_sync(kFullMask, st, QL.base);
-        new_w = __shfl_sync(kFullMask, new_w, QL.base);
-        if (need_slow) {
-          status = st;
+        status = qp_fallback4(gH, fi[0], fi[1], fi[2], fi[3], qb, &new_w);
+        if (status == 0) {
           wset = new_w;
-        } else if (pd) {
-          status = 0;
+          red_ok = qt_prepare(J, bnd, wset, red);
+          ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
+          if (!ok) status = 1;   // should not happen: KKT of the new set
         }
-        red_ok = qw_prepare(J, bnd, wset, QL, &red) && pd;
-        ok = qw_eval(red, f_row, bnd, wset, QL, &x_row, &lam_row) && red_ok;
-        if (need_slow && st == 0 && !ok) status = 1;   // should not happen: KKT of the new set
       } else if (pd) {
         status = 0;
       }
-      const double xj = qw_get(x_row, QL, QL.j, 0);
-      z_col = (status == 0) ? xj : 0.0;        // mpc_qp_solver.cc:66-69: zeros on failure
+#pragma unroll
+      for (int k = 0; k < 4; ++k) z[k] = (status == 0) ? x[k] : 0.0;   // mpc_qp_solver.cc:66-69: zeros on failure
     }
     // report of the last sweep: active constraints (strictly positive multiplier), objective
-    double fmax = fabs(f_row);
-    fmax = fmax > 1.0 ? fmax : 1.0;
-    {
-      double o = __shfl_xor_sync(kFullMask, fmax, 4);
-      fmax = fmax > o ? fmax : o;
-      o = __shfl_xor_sync(kFullMask, fmax, 8);
-      fmax = fmax > o ? fmax : o;
-    }
-    const int l = ln & 15;
-    const int wpos = __popc(wset & ((1u << l) - 1u));
-    const double lam_l = __shfl_sync(kFullMask, lam_row, QL.base + 4 * (wpos & 3));
-    const bool is_act = ((wset >> l) & 1u) && lam_l > 1e-9 * fmax && status == 0;
-    const unsigned act = (__ballot_sync(kFullMask, is_act) >> QL.base) & 0xffffu;
-    double ob = 0.5 * x_row * Hij * z_col + ((QL.j == 0) ? f_row * x_row : 0.0);
-    ob += __shfl_xor_sync(kFullMask, ob, 1);
-    ob += __shfl_xor_sync(kFullMask, ob, 2);
-    ob += __shfl_xor_sync(kFullMask, ob, 4);
-    ob += __shfl_xor_sync(kFullMask, ob, 8);
-    if (ln == QL.base) {
-      if (status == 0) G.guess[sc0 + c] = wset;
-      G.status[sc0 + c] = status;
-      G.active[sc0 + c] = status == 0 ? act : 0u;
-      G.objective[sc0 + c] = status == 0 ? ob : 0.0;
-    }
-    // du_old_ = du_prev (full plans); first moves in system order = [ctrl 0: z0 z1 | ctrl 1: z0 z1]
-    if (QL.i == 0) ss[4 + c * NV + QL.j] = z_col;
+    double fmax = 1.0, obj = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) du_sys[k] = __shfl_sync(kFullMask, z_col, 16 * (k >> 1) + (k & 1));
+    for (int i = 0; i < 4; ++i) {
+      fmax = fmax > fabs(fi[i]) ? fmax : fabs(fi[i]);
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = fma(Hm[i][k], z[k], s);
+      obj += z[i] * (0.5 * s + fi[i]);
+    }
+    unsigned act = 0, m = wset & 0xffffu;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int idx = __ffs(m) - 1;
+      m &= m - 1;
+      if (idx >= 0 && lam[w] > 1e-9 * fmax) act |= 1u << idx;
+    }
+    if (status == 0) G.guess[rec] = wset;
+    G.status[rec] = status;
+    G.active[rec] = status == 0 ? act : 0u;
+    G.objective[rec] = status == 0 ? obj : 0.0;
+    // du_old_ = du_prev; u_old_ += first move of each controller's plan (system order = ctrl 0, ctrl 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ss[4 + c * 4 + k] = z[k];
+    const double un0 = ss[2 * c] + z[0], un1 = ss[2 * c + 1] + z[1];
+    ss[2 * c] = un0;
+    ss[2 * c + 1] = un1;
+    u[size_t(scen) * 4 + 2 * c] = un0;
+    u[size_t(scen) * 4 + 2 * c + 1] = un1;
+    // each controller sees only its own inputs move (nerve_center.h:322-328)
+    const double du[4] = {z[0], z[1], 0.0, 0.0};
+    apriori_update<S>(P, G, rec, du);
   } else {
-    // generic path (centralised, 8 variables): lane c owns sub-controller c
-    const int c = ln;
-    const bool on = c < NCTRL;
-    double z[NV];
+    // centralised controller: a single controller has no plan to exchange, every sweep solves the
+    // same QP (distributed_controller.h:215-218), so one solve gives the result of all sweeps
+    static_assert(NVO == 0 && NCTRL == 1, "generic path is the centralised controller");
+    const int scen = tid;
+    if (scen >= P.batch) return;
+    double* ss = G.scen + size_t(scen) * kScenStateStride;
+    const size_t rec = size_t(scen);
+    const double* gH = G.qpH + rec * NV * NV;
+    const double* gf = G.qpf + rec * NV;
+    const double* uo = G.ctrl + rec * kCtrlStateStride + kOffUold;
+    QpData<NV> qd;
+    double f0[NV], z[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) z[i] = 0.0;
-    if (on) {
-      const double* gH = G.qpH + (sc0 + c) * NV * NV;
-      const double* gf = G.qpf + (sc0 + c) * NV;
-      const double* uo = G.ctrl + (sc0 + c) * kCtrlStateStride + kOffUold;
-      QpData<NV> qd;
-      double f0[NV];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        f0[i] = gf[i];
-        qd.lb[i] = P.c[0].lower[i % NU] - uo[i % NU];
-        qd.ub[i] = P.c[0].upper[i % NU] - uo[i % NU];
-        qd.lbA[i] = P.c[0].rate_lower[i % NU];
-        qd.ubA[i] = P.c[0].rate_upper[i % NU];
-      }
-      unsigned wset = G.guess[sc0 + c], act = 0;
-      double obj = 0.0;
-      int status = 3;
-      if (qp_invert_spd<NV>(gH, qd.J)) {
-        // a single controller has no plan to exchange: every sweep solves the same QP
-        // (distributed_controller.h:215-218), so one solve gives the result of all n_iter sweeps
-        static_assert(NVO == 0, "generic path is the centralised controller");
-        status = qp_solve<NV, NU>(qd, gH, f0, &wset, z, &act, &obj);
-      }
-      if (status != 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) z[i] = 0.0;
-      } else {
-        G.guess[sc0 + c] = wset;
-      }
-      G.status[sc0 + c] = status;
-      G.active[sc0 + c] = status == 0 ? act : 0u;
-      G.objective[sc0 + c] = status == 0 ? obj : 0.0;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) ss[4 + c * NV + i] = z[i];
+    for (int i = 0; i < NV; ++i) {
+      f0[i] = gf[i];
+      z[i] = 0.0;
+      qd.lb[i] = P.c[0].lower[i % NU] - uo[i % NU];
+      qd.ub[i] = P.c[0].upper[i % NU] - uo[i % NU];
+      qd.lbA[i] = P.c[0].rate_lower[i % NU];
+      qd.ubA[i] = P.c[0].rate_upper[i % NU];
     }
+    unsigned wset = G.guess[rec], act = 0;
+    double obj = 0.0;
+    int status = 3;
+    if (qp_invert_spd<NV>(gH, qd.J)) status = qp_solve<NV, NU>(qd, gH, f0, &wset, z, &act, &obj);
+    if (status != 0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) du_sys[k] = __shfl_sync(kFullMask, z[k < NU ? k : 0], 0);
+      for (int i = 0; i < NV; ++i) z[i] = 0.0;
+    } else {
+      G.guess[rec] = wset;
+    }
+    G.status[rec] = status;
+    G.active[rec] = status == 0 ? act : 0u;
+    G.objective[rec] = status == 0 ? obj : 0.0;
+    double du[4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ss[4 + i] = z[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      du[k] = z[k];
+      const double un = ss[k] + z[k];
+      ss[k] = un;
+      u[size_t(scen) * 4 + k] = un;
+    }
+    apriori_update<S>(P, G, rec, du);
   }
-
-  // nerve_center.h:162-167,313-319: u_old_ += first move of each controller's plan
-#pragma unroll
-  for (int k = 0; k < 4; ++k) u_new[k] = ss[k] + du_sys[k];
-  __syncwarp();
-  if (ln < 4) ss[ln] = sel4(u_new, ln);
-  // UpdateU / ObserveAPriori for every controller: each sees only its own inputs move
-  // (nerve_center.h:322-328); lanes split the augmented state
-  for (int c = 0; c < NCTRL; ++c) {
-    double* gs = G.ctrl + (sc0 + c) * kCtrlStateStride;
-    const double* BF = G.work + (sc0 + c) * kWorkStride + kWBF;
-    double du[4] = {0.0, 0.0, 0.0, 0.0}, uold[4];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) du[i] = sel4(du_sys, c * NU + i);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) uold[i] = gs[kOffUold + i];
-    const double h0 = gs[kOffDx + NOBS + 0] - uold[1], h1 = gs[kOffDx + NOBS + 1] - uold[3];
-    constexpr int PER = (NTOT + 31) / 32;
-    double nv[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int i = ln + 32 * k;
-      double v = 0.0;
-      if (i < N) {
-        v = BF[i * kNC + 0] * du[0] + BF[i * kNC + 2] * du[2] + BF[i * kNC + 1] * h0 +
-            BF[i * kNC + 3] * h1 + BF[i * kNC + 4];
-      } else if (i < NOBS) {
-        v = gs[kOffDx + i];
-      } else if (i < NOBS + 2) {
-        v = gs[kOffDx + NOBS + 2 + (i - NOBS) * (kDelay - 1)];  // head <- first chain slot
-      } else if (i < NTOT) {
-        const int cidx = i - NOBS - 2, d = cidx / (kDelay - 1), jj = cidx % (kDelay - 1);
-        v = (jj == kDelay - 2) ? uold[1 + 2 * d] + du[1 + 2 * d] : gs[kOffDx + i + 1];
-      }
-      nv[k] = v;
-    }
-    __syncwarp();   // every lane has read the old delay line before anyone overwrites it
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int i = ln + 32 * k;
-      if (i < NTOT) gs[kOffDx + i] = nv[k];
-    }
-    if (ln < 4) gs[kOffUold + ln] = uold[ln] + du[ln];
-  }
-}
-
-template <class S>
-__global__ void __launch_bounds__(128, S::NV == 4 ? CMPC_SOLVE_MIN_BLOCKS : 2)
-solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
-  const int ln = threadIdx.x & 31;
-  const int scen = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (scen >= P.batch) return;
-  double u_new[4];
-  solve_and_update<S>(P, G, scen, ln, u_new);
-  if (ln < 4) u[size_t(scen) * 4 + ln] = sel4(u_new, ln);
 }
 
 }  // namespace cmpc
