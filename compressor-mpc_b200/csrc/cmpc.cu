@@ -102,6 +102,9 @@ template <class S>
 int shape_setup(cmpc_handle* h) {
   const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow);
   h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 8);
+#ifdef CMPC_PHASE_TIMING
+  if (const char* e = getenv("CMPC_DEBUG_SMEM_MIN")) { size_t m = size_t(atol(e)); if (h->smem_bytes < m) h->smem_bytes = m; }  // occupancy experiments
+#endif
   if (h->smem_bytes > 227 * 1024)
     return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
   CU(cudaFuncSetAttribute(assemble_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));

@@ -126,7 +126,7 @@ __host__ __device__ inline int giant_stride(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int yv, dxd, q, Cc, BF, carry, U, cz, region, L, R, V, lr_end, E, total;
+  int yv, dxd, q, Cc, BF, carry, U, cz, region, L, R, V, lr_end, E, ldE, total;
   bool e_alias;
   __host__ __device__ SmemLayout(int p, int b_max, int n_pow) {
     int o = 0;
@@ -145,7 +145,10 @@ struct SmemLayout {
     R = L + kBaby * S::NY * kLD;
     V = R + kLD * giant_stride(b_max);      // 12 rows: rows >= N stay zero (K padding)
     lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
-    const int e_size = kBaby * b_max * S::NCH;
+    // E is channel-major: E[(y kNC + c) ldE + r].  ldE = 2 mod 4 keeps the 16-byte row-pair loads of
+    // phase 6 aligned and spreads the four column pairs of a DMMA output tile over all banks.
+    ldE = kBaby * b_max + 2;
+    const int e_size = S::NCH * ldE;
     const int red_size = S::TPC * (S::NACC | 1);
     // E can overwrite its own inputs when every warp can hold its output tiles in registers
     const int n_nt = (b_max * kNC + 7) / 8;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
 assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
-  constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NCH = S::NCH, NSC = S::NSC, NH = S::NH;
+  constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NSC = S::NSC, NH = S::NH;
 #ifdef CMPC_PHASE_TIMING
   const long long tick_t0_ = clock64();
 #endif
@@ -335,6 +338,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int lane = t & 31, warp = t >> 5;
   const int p = P.p, b_max = P.b_max, ldr = P.ldr;
   const SmemLayout<S> lay(p, b_max, P.n_pow);
+  const int ldE = lay.ldE;
   double* sm = smem + g * lay.total;
   const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
@@ -438,12 +442,13 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 
   CMPC_TICK(1);
   // ---- phase 4: powers Ad^(2^j) with baby (L), giant (R) and delay (V) steps by doubling ----
-  // L_a = C~ Ad^a (a < 8): rows [2^j, 2^(j+1)) = rows [0, 2^j) * Ad^(2^j), j = 0..2
+  // L_a = C~ Ad^a (a < 8), stored output-major (row 8 y + a): rows a in [2^j, 2^(j+1)) =
+  //       rows a in [0, 2^j) * Ad^(2^j), j = 0..2
   // V_a = Ad^a Bd[:, delayed] (a < 8), same doubling on the left
   // R_b = Ad^(8b) [Bd fd X40]: blocks [2^j, 2^(j+1)) = Ad^(8*2^j) * blocks [0, 2^j), j = 0..
   // X40 = state reached after the 40 queued delayed inputs have been applied (free response
   // of the delay line): conv[r] = C~ Ad^(r-39) X40 for r >= 39 comes out of the same table.
-  for (int idx = t; idx < NY * N; idx += TPC) L[(idx / N) * kLD + idx % N] = Cc[P.c[g].out_idx[idx / N] * N + idx % N];
+  for (int idx = t; idx < NY * N; idx += TPC) L[(idx / N) * kBaby * kLD + idx % N] = Cc[P.c[g].out_idx[idx / N] * N + idx % N];
   for (int idx = t; idx < N * 5; idx += TPC) R[(idx / 5) * ldr + idx % 5] = BF[(idx / 5) * kNC + idx % 5];
   for (int idx = t; idx < N * 2; idx += TPC) V[(idx >> 1) * kLDV + (idx & 1)] = BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)];
   group_sync(g, TPC);
@@ -501,17 +506,34 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     frag_b(Pm, kLD, 0, lane, bq[0]);
     frag_b(Pm, kLD, 1, lane, bq[1]);
     if (j < 3) {
-      const int vc = 2 << j, l_rows = (1 << j) * NY, n_lm = (l_rows + 7) >> 3;
+      const int vc = 2 << j, l_cnt = 1 << j, n_lm = (l_cnt * NY + 7) >> 3;
       frag_b(V, kLDV, 0, lane, bq[2]);
       double al[2][3], bl[3], cl[2][2];
       frag_b(Pm, kLD, mt_w, lane, bl);      // column block nt = w of Pm
-      frag_a(L, kLD, 0, lane, al[0]);
-      frag_a(L, kLD, 1, lane, al[1]);
+      // fragment row i of the doubling is (y, a) = (i >> j, i mod 2^j), i.e. row 8 y + a of L
+      int l_row[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int i = 8 * mt + (lane >> 2), yy = i >> j;
+        l_row[mt] = (yy < NY) ? kBaby * yy + (i & (l_cnt - 1)) : -1;
+        const double* pl = L + (l_row[mt] < 0 ? 0 : l_row[mt]) * kLD + (lane & 3);
+        al[mt][0] = pl[0];
+        al[mt][1] = pl[4];
+        al[mt][2] = pl[8];
+      }
       mma3_shared_a<6>(cq, a, bq, 3);
       mma3_shared_b<2>(cl, al, bl, n_lm);
       tile_store(V, kLDV, 0, vc, N, vc, mt_w, 0, lane, cq[2]);
-      tile_store(L, kLD, l_rows, 0, l_rows, kLD, 0, mt_w, lane, cl[0]);
-      if (n_lm > 1) tile_store(L, kLD, l_rows, 0, l_rows, kLD, 1, mt_w, lane, cl[1]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int cc = 8 * mt_w + 2 * (lane & 3);
+        if (mt < n_lm && l_row[mt] >= 0 && cc < kLD) {
+          double2 v;
+          v.x = cl[mt][0];
+          v.y = cl[mt][1];
+          *reinterpret_cast<double2*>(L + (l_row[mt] + l_cnt) * kLD + cc) = v;
+        }
+      }
     } else {
       const int r_base = 1 << (j - 3);
       int cnt = r_base;
@@ -553,14 +575,15 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     double al[NY][3];
 #pragma unroll
     for (int mt = 0; mt < NY; ++mt) frag_a(L, kLD, mt, lane, al[mt]);
+    // row block mt of L is output mt, its rows are the baby steps a: a lane's two results are
+    // channels (cc, cc + 1) of row a + 8 b (cc is even, so both stay inside block b)
     auto store_e = [&](int mt, int nt, const double (&c)[2]) {
-      const int m = 8 * mt + (lane >> 2), n = 8 * nt + 2 * (lane & 3);
+      const int a = lane >> 2, n = 8 * nt + 2 * (lane & 3);
       if (n < b_max * kNC) {
-        const int a = m / NY, y = m % NY, b = n / kNC, cc = n % kNC;
-        double2 v;
-        v.x = c[0];
-        v.y = c[1];
-        *reinterpret_cast<double2*>(E + (a + kBaby * b) * NCH + y * kNC + cc) = v;
+        const int b = n / kNC, cc = n % kNC;
+        double* e = E + (mt * kNC + cc) * ldE + kBaby * b + a;
+        e[0] = c[0];
+        e[ldE] = c[1];
       }
     };
     if (warp == WPC - 1) {
@@ -571,8 +594,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 #pragma unroll
       for (int mt = 0; mt < NY; ++mt) {
         const double (&cz)[2] = czz[mt];
-        const int m = 8 * mt + (lane >> 2), n = 2 * (lane & 3);
-        const int a = m / NY, y = m % NY;
+        const int a = lane >> 2, y = mt, n = 2 * (lane & 3);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int r = 8 * (n + e) + a - 1;
@@ -614,7 +636,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   group_sync(g, TPC);
   if (G.etab) {
     double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NY * 5);
-    for (int idx = t; idx < p * NY * 5; idx += TPC) ge[idx] = E[(idx / 5) * kNC + idx % 5];
+    for (int idx = t; idx < p * NY * 5; idx += TPC)
+      ge[idx] = E[(((idx / 5) % NY) * kNC + idx % 5) * ldE + idx / (5 * NY)];
   }
 
   CMPC_TICK(3);
@@ -625,30 +648,40 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   //   H = Su' Q Su + R, Gx = Su' Q Su_other, f = Su' Q w accumulated per thread, then reduced.
   // RPT = rows per thread (compile time): 2 covers p <= 128, 4 covers p <= 256
   const int r0 = t * RPT;
-  const int r1 = (r0 + RPT < p) ? r0 + RPT : p;
-  auto load_g = [&](int r, double* gv) {
-    const double* Er = E + r * NCH;
-    const bool del = r >= kDelay;
-    const double* Ed = E + (del ? r - kDelay : 0) * NCH;
+  // the thread's RPT rows of every channel come in as 16-byte row pairs (r0 and kDelay are
+  // multiples of RPT, so the pairs of the delayed columns are aligned too)
+  auto load_g = [&](double (&gv)[RPT][NSC]) {
+    const bool on = r0 < p, del = r0 >= kDelay;
 #pragma unroll
-    for (int y = 0; y < NY; ++y) {
-      gv[y * kNS + 0] = Er[y * kNC + 0];
-      gv[y * kNS + 1] = del ? Ed[y * kNC + 1] : 0.0;
-      gv[y * kNS + 2] = Er[y * kNC + 2];
-      gv[y * kNS + 3] = del ? Ed[y * kNC + 3] : 0.0;
-      gv[y * kNS + 4] = Er[y * kNC + 4];
-    }
+    for (int y = 0; y < NY; ++y)
+#pragma unroll
+      for (int c = 0; c < kNS; ++c) {
+        const bool delayed = (c == 1 || c == 3);
+        const bool ld = on && (!delayed || del);
+        const double* src = E + (y * kNC + c) * ldE + r0 - ((delayed && del) ? kDelay : 0);
+#pragma unroll
+        for (int j = 0; j < RPT; j += 2) {
+          double2 v = make_double2(0.0, 0.0);
+          if (ld) v = *reinterpret_cast<const double2*>(src + j);
+          gv[j][y * kNS + c] = v.x;
+          gv[j + 1][y * kNS + c] = v.y;
+        }
+      }
   };
   double off[NSC];
   {
     double tot[NSC];
 #pragma unroll
     for (int c = 0; c < NSC; ++c) tot[c] = 0.0;
-    for (int r = r0; r < r1; ++r) {
-      double gv[NSC];
-      load_g(r, gv);
+    {
+      double gv[RPT][NSC];
+      load_g(gv);
 #pragma unroll
-      for (int c = 0; c < NSC; ++c) tot[c] += gv[c];
+      for (int j = 0; j < RPT; ++j)
+        if (r0 + j < p) {
+#pragma unroll
+          for (int c = 0; c < NSC; ++c) tot[c] += gv[j][c];
+        }
     }
 #pragma unroll
     for (int c = 0; c < NSC; ++c) {
@@ -679,16 +712,17 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     if (r < p) {
       if (r >= kDelay - 1) {
 #pragma unroll
-        for (int y = 0; y < NY; ++y) conv[j][y] = E[(r - (kDelay - 1)) * NCH + y * kNC + 5];
+        for (int y = 0; y < NY; ++y) conv[j][y] = E[(y * kNC + 5) * ldE + r - (kDelay - 1)];
       } else {
         const int bb = (r + 1) >> 3, aa = (r + 1) & 7;
 #pragma unroll
         for (int y = 0; y < NY; ++y) conv[j][y] = CZ[r * NY + y];
         for (int i = 0; i < aa; ++i) {
-          const double* Ek = E + (aa - 1 - i) * NCH;
+          const double* Ek = E + (aa - 1 - i);
           const double q0 = q[8 * bb + i], q1 = q[kDelay + 8 * bb + i];
 #pragma unroll
-          for (int y = 0; y < NY; ++y) conv[j][y] = fma(Ek[y * kNC + 1], q0, fma(Ek[y * kNC + 3], q1, conv[j][y]));
+          for (int y = 0; y < NY; ++y)
+            conv[j][y] = fma(Ek[(y * kNC + 1) * ldE], q0, fma(Ek[(y * kNC + 3) * ldE], q1, conv[j][y]));
         }
       }
     }
@@ -701,8 +735,18 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   for (int j = 0; j < RPT; ++j) {
     const int r = r0 + j;
     if (r < p) {
+      // one row at a time (8-byte loads): both rows of a pair would not fit the register budget
       double gv[NSC], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
-      load_g(r, gv);
+      {
+        const bool del = r >= kDelay;
+#pragma unroll
+        for (int y = 0; y < NY; ++y)
+#pragma unroll
+          for (int c = 0; c < kNS; ++c) {
+            const bool delayed = (c == 1 || c == 3);
+            gv[y * kNS + c] = (!delayed || del) ? E[(y * kNC + c) * ldE + r - (delayed ? kDelay : 0)] : 0.0;
+          }
+      }
 #pragma unroll
       for (int y = 0; y < NY; ++y) {
 #pragma unroll
