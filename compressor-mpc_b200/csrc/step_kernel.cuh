@@ -29,6 +29,7 @@
 // steps R_b = Ad^(8b) [Bd | fd], both obtained by repeated squaring/doubling, so the
 // sequential depth is ~log2(p) small matrix products instead of p.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -55,6 +56,7 @@ constexpr int kWorkStride = 512, kWAc = 0, kWXc = 144, kWCc = 288, kWBF = 336;
 // kWBF holds what the a-priori observer update needs: base[N] (free response of the state part),
 // then the Bd columns of the undelayed inputs 0 and 2 (N each)
 constexpr int kRing = kDelay - 1;   // slots of one delay ring (the head is kept separately)
+constexpr int kMaxPow = 8;           // stages of the power ladder: horizons up to 8 * 2^5 = 256
 constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
 
 // offsets inside one controller's global state record
@@ -193,38 +195,69 @@ __device__ __forceinline__ void mma3(double (&c)[2], const double (&a)[3], const
 }
 // NT independent tiles sharing the A fragments (one row block times NT column blocks): the DMMAs
 // of different tiles are interleaved so that no instruction waits for the previous one.
+// Tiles [LO, HI) are computed, as straight-line code: a run-time tile count must be turned into
+// one of these by a switch (mma3_shared_a / _b below).  A predicate per DMMA would let the compiler
+// speculate the masked tiles, and every DMMA occupies the FP64 pipe of its SM sub-partition for
+// ~16 cycles whether its result is used or not.
+template <int NT, int LO, int HI>
+__device__ __forceinline__ void mma3_shared_a_range(double (&c)[NT][2], const double (&a)[3], const double (&b)[NT][3]) {
+#pragma unroll
+  for (int i = LO; i < HI; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+    for (int i = LO; i < HI; ++i) dmma_884(c[i], a[kt], b[i][kt]);
+}
 template <int NT>
 __device__ __forceinline__ void mma3_shared_a(double (&c)[NT][2], const double (&a)[3], const double (&b)[NT][3], int n_on = NT) {
-#pragma unroll
-  for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = 0.0;
-#pragma unroll
-  for (int kt = 0; kt < 3; ++kt)
-#pragma unroll
-    for (int i = 0; i < NT; ++i)
-      if (i < n_on) dmma_884(c[i], a[kt], b[i][kt]);
+  static_assert(NT <= 6, "tile count");
+  switch (n_on) {
+    case 1: mma3_shared_a_range<NT, 0, 1>(c, a, b); break;
+    case 2: if constexpr (NT >= 2) mma3_shared_a_range<NT, 0, 2>(c, a, b); break;
+    case 3: if constexpr (NT >= 3) mma3_shared_a_range<NT, 0, 3>(c, a, b); break;
+    case 4: if constexpr (NT >= 4) mma3_shared_a_range<NT, 0, 4>(c, a, b); break;
+    case 5: if constexpr (NT >= 5) mma3_shared_a_range<NT, 0, 5>(c, a, b); break;
+    case 6: if constexpr (NT >= 6) mma3_shared_a_range<NT, 0, 6>(c, a, b); break;
+    default: break;
+  }
 }
 // NT independent tiles sharing the B fragments (NT row blocks times one column block)
-template <int NT>
-__device__ __forceinline__ void mma3_shared_b(double (&c)[NT][2], const double (&a)[NT][3], const double (&b)[3], int n_on = NT) {
+template <int NT, int HI>
+__device__ __forceinline__ void mma3_shared_b_range(double (&c)[NT][2], const double (&a)[NT][3], const double (&b)[3]) {
 #pragma unroll
-  for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int i = 0; i < HI; ++i) c[i][0] = c[i][1] = 0.0;
 #pragma unroll
   for (int kt = 0; kt < 3; ++kt)
 #pragma unroll
-    for (int i = 0; i < NT; ++i)
-      if (i < n_on) dmma_884(c[i], a[i][kt], b[kt]);
+    for (int i = 0; i < HI; ++i) dmma_884(c[i], a[i][kt], b[kt]);
+}
+template <int NT>
+__device__ __forceinline__ void mma3_shared_b(double (&c)[NT][2], const double (&a)[NT][3], const double (&b)[3], int n_on = NT) {
+  static_assert(NT <= 4, "tile count");
+  switch (n_on) {
+    case 1: mma3_shared_b_range<NT, 1>(c, a, b); break;
+    case 2: if constexpr (NT >= 2) mma3_shared_b_range<NT, 2>(c, a, b); break;
+    case 3: if constexpr (NT >= 3) mma3_shared_b_range<NT, 3>(c, a, b); break;
+    case 4: if constexpr (NT >= 4) mma3_shared_b_range<NT, 4>(c, a, b); break;
+    default: break;
+  }
 }
 
 // Store a tile into a row-major matrix C (even stride, even column offset) as one 16-byte store
 // per lane.  Rows >= mc and column pairs starting at >= nc_pad are dropped (nc_pad even; a pad
 // column inside the pair receives an exact zero because the B operand's pad column is zero).
+template <bool ADD_EYE = false>
 __device__ __forceinline__ void tile_store(double* C, int ldc, int row_off, int col_off, int mc, int nc_pad,
-                                           int mt, int nt, int lane, const double (&c)[2], bool add_eye = false) {
+                                           int mt, int nt, int lane, const double (&c)[2]) {
   const int r = 8 * mt + (lane >> 2), cc = 8 * nt + 2 * (lane & 3);
   if (r < mc && cc < nc_pad) {
     double2 v;
-    v.x = c[0] + ((add_eye && r == cc) ? 1.0 : 0.0);
-    v.y = c[1] + ((add_eye && r == cc + 1) ? 1.0 : 0.0);
+    v.x = c[0];
+    v.y = c[1];
+    if (ADD_EYE) {
+      if (r == cc) v.x += 1.0;
+      if (r == cc + 1) v.y += 1.0;
+    }
     *reinterpret_cast<double2*>(C + (row_off + r) * ldc + col_off + cc) = v;
   }
 }
@@ -428,8 +461,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     // Ad = I + Acom Ac (into the A2 slot), [Bd | fd] = Acom Xc
     frag_a(Acom, kLD, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 3);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0], true);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1], true);
+    tile_store<true>(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0]);
+    tile_store<true>(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1]);
     tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
     group_sync(g, TPC);
   }
@@ -452,11 +485,14 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   for (int idx = t; idx < N * 5; idx += TPC) R[(idx / 5) * ldr + idx % 5] = BF[(idx / 5) * kNC + idx % 5];
   for (int idx = t; idx < N * 2; idx += TPC) V[(idx >> 1) * kLDV + (idx & 1)] = BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)];
   group_sync(g, TPC);
-  for (int s = 1; s <= P.n_pow; ++s) {
-    const int j = s - 1;
+  // The stages are unrolled with a compile-time index: every stage but the last one of the run has
+  // compile-time tile counts, so its DMMAs are straight-line code with nothing to predicate.
+  auto stage = [&](auto Jc) {
+    constexpr int j = decltype(Jc)::value, s = j + 1;
+    if (s > P.n_pow) return;
     const double* Pm = Pw + j * kNNP;
     double* Pn = Pw + s * kNNP;
-    if (j == 3) {
+    if constexpr (j == 3) {
       // X40 = P(P(P(P U_0 + U_1) + U_2) + U_3) + U_4 with U_b = sum_{a,d} V_(7-a)[:, d] q_d[8b + a],
       // P = Ad^8 = Pm.  Warp 0 of the group, lanes 0..N-1 hold one state each.
       for (int idx = t; idx < 5 * N; idx += TPC) {
@@ -495,25 +531,25 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         if (lane < N) R[lane * ldr + 5] = z;
       }
       group_sync(g, TPC);
+      CMPC_TICK(8);
     }
-    if (j == 3) CMPC_TICK(8);
     // this warp's row block of Pm multiplies: Pm (squaring), V (j < 3), R (j >= 3);
     // its column block of Pm is multiplied by the rows of L (j < 3).  All products of a stage
     // are independent: their DMMAs are issued interleaved.
-    double a[3], bq[6][3], cq[6][2];   // tiles 0,1: squaring; 2..5: V (j < 3) or column blocks of R
+    double a[3];
     frag_a(Pm, kLD, mt_w, lane, a);
-    const bool do_sq = s < P.n_pow;    // (the last stage squares once more than needed; its result is dropped)
-    frag_b(Pm, kLD, 0, lane, bq[0]);
-    frag_b(Pm, kLD, 1, lane, bq[1]);
-    if (j < 3) {
-      const int vc = 2 << j, l_cnt = 1 << j, n_lm = (l_cnt * NY + 7) >> 3;
+    if constexpr (j < 3) {
+      constexpr int vc = 2 << j, l_cnt = 1 << j, n_lm = (l_cnt * NY + 7) >> 3;
+      double bq[3][3], cq[3][2];   // tiles 0,1: squaring; 2: V
+      frag_b(Pm, kLD, 0, lane, bq[0]);
+      frag_b(Pm, kLD, 1, lane, bq[1]);
       frag_b(V, kLDV, 0, lane, bq[2]);
       double al[2][3], bl[3], cl[2][2];
       frag_b(Pm, kLD, mt_w, lane, bl);      // column block nt = w of Pm
       // fragment row i of the doubling is (y, a) = (i >> j, i mod 2^j), i.e. row 8 y + a of L
       int l_row[2];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < n_lm; ++mt) {
         const int i = 8 * mt + (lane >> 2), yy = i >> j;
         l_row[mt] = (yy < NY) ? kBaby * yy + (i & (l_cnt - 1)) : -1;
         const double* pl = L + (l_row[mt] < 0 ? 0 : l_row[mt]) * kLD + (lane & 3);
@@ -521,51 +557,76 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         al[mt][1] = pl[4];
         al[mt][2] = pl[8];
       }
-      mma3_shared_a<6>(cq, a, bq, 3);
-      mma3_shared_b<2>(cl, al, bl, n_lm);
+      mma3_shared_a_range<3, 0, 3>(cq, a, bq);
+      mma3_shared_b_range<2, n_lm>(cl, al, bl);
       tile_store(V, kLDV, 0, vc, N, vc, mt_w, 0, lane, cq[2]);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < n_lm; ++mt) {
         const int cc = 8 * mt_w + 2 * (lane & 3);
-        if (mt < n_lm && l_row[mt] >= 0 && cc < kLD) {
+        if (l_row[mt] >= 0 && cc < kLD) {
           double2 v;
           v.x = cl[mt][0];
           v.y = cl[mt][1];
           *reinterpret_cast<double2*>(L + (l_row[mt] + l_cnt) * kLD + cc) = v;
         }
       }
-    } else {
-      const int r_base = 1 << (j - 3);
-      int cnt = r_base;
-      if (r_base + cnt > b_max) cnt = b_max - r_base;
-      const int r_cols = cnt > 0 ? cnt * kNC : 0;
-      const int n_rt = (r_cols + 7) >> 3;
-      // the first (up to) 4 column blocks of R are interleaved with the squaring
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < n_rt) frag_b(R, ldr, i, lane, bq[2 + i]);
-      mma3_shared_a<6>(cq, a, bq, 2 + (n_rt < 4 ? n_rt : 4));
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, i, lane, cq[2 + i]);
-      // wider stages (long horizons): remaining column blocks, four at a time
-      for (int nt0 = 4; nt0 < n_rt; nt0 += 4) {
-        double bw[4][3], cw[4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (nt0 + i < n_rt) frag_b(R, ldr, nt0 + i, lane, bw[i]);
-        mma3_shared_a<4>(cw, a, bw, n_rt - nt0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt0 + i, lane, cw[i]);
-      }
-    }
-    if (do_sq) {
       tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 0, lane, cq[0]);
       tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 1, lane, cq[1]);
+    } else {
+      constexpr int r_base = 1 << (j - 3);
+      if (s < P.n_pow) {
+        // full doubling: column blocks [r_base, 2 r_base) = Pm * blocks [0, r_base); the first
+        // (up to) 4 column tiles are interleaved with the squaring
+        constexpr int r_cols = r_base * kNC, n_rt = (r_cols + 7) >> 3, n_first = n_rt < 4 ? n_rt : 4;
+        double bq[2 + n_first][3], cq[2 + n_first][2];
+        frag_b(Pm, kLD, 0, lane, bq[0]);
+        frag_b(Pm, kLD, 1, lane, bq[1]);
+#pragma unroll
+        for (int i = 0; i < n_first; ++i) frag_b(R, ldr, i, lane, bq[2 + i]);
+        mma3_shared_a_range<2 + n_first, 0, 2 + n_first>(cq, a, bq);
+#pragma unroll
+        for (int i = 0; i < n_first; ++i) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, i, lane, cq[2 + i]);
+        tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 0, lane, cq[0]);
+        tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 1, lane, cq[1]);
+#pragma unroll
+        for (int nt0 = 4; nt0 < n_rt; nt0 += 4) {
+          double bw[4][3], cw[4][2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (nt0 + i < n_rt) frag_b(R, ldr, nt0 + i, lane, bw[i]);
+          mma3_shared_a<4>(cw, a, bw, n_rt - nt0 < 4 ? n_rt - nt0 : 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt0 + i, lane, cw[i]);
+        }
+      } else {
+        // last stage of the run: only the blocks up to b_max, and no further power
+        const int cnt = b_max - r_base;
+        const int r_cols = cnt > 0 ? cnt * kNC : 0;
+        const int n_rt = (r_cols + 7) >> 3;
+        for (int nt0 = 0; nt0 < n_rt; nt0 += 6) {
+          double bw[6][3], cw[6][2];
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            if (nt0 + i < n_rt) frag_b(R, ldr, nt0 + i, lane, bw[i]);
+          mma3_shared_a<6>(cw, a, bw, n_rt - nt0 < 6 ? n_rt - nt0 : 6);
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt0 + i, lane, cw[i]);
+        }
+      }
     }
     group_sync(g, TPC);
-  }
+  };
+  stage(std::integral_constant<int, 0>{});
+  stage(std::integral_constant<int, 1>{});
+  stage(std::integral_constant<int, 2>{});
+  stage(std::integral_constant<int, 3>{});
+  stage(std::integral_constant<int, 4>{});
+  stage(std::integral_constant<int, 5>{});
+  stage(std::integral_constant<int, 6>{});
+  stage(std::integral_constant<int, 7>{});
+  static_assert(kMaxPow == 8, "one stage call per power");
 
   CMPC_TICK(2);
   // ---- phase 5: E[a + 8b][y][c] = (L_a R_b)[y][c]: (8 NY x N) (N x b_max kNC) on the tensor cores ----
