@@ -98,6 +98,16 @@ int find_shape(const cmpc_config& c) {
   return -1;
 }
 
+// The assemble_kernel instantiation for a prediction horizon: compile-time horizons for the
+// reference's p = 100 and the 2x sweep, run-time horizon otherwise.
+using AssembleFn = void (*)(StepParams, DeviceState, const double*);
+template <class S>
+AssembleFn assemble_variant(int p) {
+  if (p == 100) return assemble_kernel<S, 2, 100>;
+  if (p == 200) return assemble_kernel<S, 4, 200>;
+  return p <= 2 * S::TPC ? assemble_kernel<S, 2, 0> : assemble_kernel<S, 4, 0>;
+}
+
 template <class S>
 int shape_setup(cmpc_handle* h) {
   const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow);
@@ -107,16 +117,15 @@ int shape_setup(cmpc_handle* h) {
 #endif
   if (h->smem_bytes > 227 * 1024)
     return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
-  CU(cudaFuncSetAttribute(assemble_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
-  CU(cudaFuncSetAttribute(assemble_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  const AssembleFn fn = assemble_variant<S>(h->P.p);
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
   // ask for the largest shared-memory carveout: occupancy of this kernel is bounded by shared memory
-  CU(cudaFuncSetAttribute(assemble_kernel<S, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CU(cudaFuncSetAttribute(assemble_kernel<S, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (getenv("CMPC_DEBUG")) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, assemble_kernel<S, 2>, S::NCTRL * S::TPC, h->smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, S::NCTRL * S::TPC, h->smem_bytes);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, assemble_kernel<S, 2>);
+    cudaFuncGetAttributes(&fa, fn);
     fprintf(stderr, "[cmpc] assemble_kernel: smem %zu B/CTA, %d regs, %zu B local, occupancy %d CTAs/SM\n",
             h->smem_bytes, fa.numRegs, fa.localSizeBytes, nb);
   }
@@ -153,10 +162,7 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
   lin_kernel<S><<<(n_thr + 127) / 128, 128, 0, st>>>(h->P, h->G, y);
   if (ev) CU(cudaEventRecord(ev[1], st));
   // K1: discretisation, prediction, QP assembly; one CTA per scenario
-  if (h->cfg.p <= 2 * S::TPC)
-    assemble_kernel<S, 2><<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
-  else
-    assemble_kernel<S, 4><<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
+  assemble_variant<S>(h->cfg.p)<<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
   if (ev) CU(cudaEventRecord(ev[2], st));
   // K2: Jacobi sweeps + update; one warp per scenario
   solve_kernel<S><<<(B * S::NCTRL + 63) / 64, 64, 0, st>>>(h->P, h->G, u);
@@ -307,9 +313,7 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   StepParams& P = h->P;
   P.p = cfg->p;
   P.b_max = (cfg->p + kBaby - 1) / kBaby;
-  int lg = 0;
-  while ((1 << lg) < P.b_max) ++lg;
-  P.n_pow = 3 + lg;
+  P.n_pow = ladder_stages(P.b_max);
   P.ldr = giant_stride(P.b_max);
   P.n_iter = cfg->n_iterations;
   P.batch = cfg->batch;

@@ -118,10 +118,17 @@ __device__ __forceinline__ void group_sync(int g, int nthreads) {
 
 // Row stride of the giant-step matrix R (N x b_max*kNC): >= the column count and = 4 or 12
 // mod 16 so that the DMMA B-fragment loads (4 rows x 4 columns per half warp) hit 16 banks.
-__host__ __device__ inline int giant_stride(int b_max) {
+__host__ __device__ constexpr int giant_stride(int b_max) {
   int ld = b_max * kNC;
   while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
   return ld;
+}
+
+// Stages of the power ladder for b_max giant steps: 3 baby doublings + ceil(log2(b_max)).
+__host__ __device__ constexpr int ladder_stages(int b_max) {
+  int lg = 0;
+  while ((1 << lg) < b_max) ++lg;
+  return 3 + lg;
 }
 
 // Shared-memory footprint of one controller group, in doubles.  The big region is used three
@@ -356,7 +363,10 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 #endif
 
 // ---- K1: discretisation, prediction and QP assembly of one scenario per CTA --------------------
-template <class S, int RPT>
+// PCT > 0 fixes the prediction horizon at compile time (the reference's p = 100 and the 2x sweep):
+// every tile count, stride and loop bound below then folds to a constant.  PCT = 0 reads them
+// from the parameters.
+template <class S, int RPT, int PCT>
 __global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
 assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
@@ -369,8 +379,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   if (scen >= P.batch) return;
   const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
   const int lane = t & 31, warp = t >> 5;
-  const int p = P.p, b_max = P.b_max, ldr = P.ldr;
-  const SmemLayout<S> lay(p, b_max, P.n_pow);
+  constexpr bool CT = PCT > 0;
+  constexpr int kBmaxCt = (PCT + kBaby - 1) / kBaby;
+  const int p = CT ? PCT : P.p, b_max = CT ? kBmaxCt : P.b_max;
+  const int ldr = CT ? giant_stride(kBmaxCt) : P.ldr, n_pow = CT ? ladder_stages(kBmaxCt) : P.n_pow;
+  const SmemLayout<S> lay(p, b_max, n_pow);
   const int ldE = lay.ldE;
   double* sm = smem + g * lay.total;
   const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
@@ -489,7 +502,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // compile-time tile counts, so its DMMAs are straight-line code with nothing to predicate.
   auto stage = [&](auto Jc) {
     constexpr int j = decltype(Jc)::value, s = j + 1;
-    if (s > P.n_pow) return;
+    if (s > n_pow) return;
     const double* Pm = Pw + j * kNNP;
     double* Pn = Pw + s * kNNP;
     if constexpr (j == 3) {
@@ -574,7 +587,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 1, lane, cq[1]);
     } else {
       constexpr int r_base = 1 << (j - 3);
-      if (s < P.n_pow) {
+      if (s < n_pow) {
         // full doubling: column blocks [r_base, 2 r_base) = Pm * blocks [0, r_base); the first
         // (up to) 4 column tiles are interleaved with the squaring
         constexpr int r_cols = r_base * kNC, n_rt = (r_cols + 7) >> 3, n_first = n_rt < 4 ? n_rt : 4;

@@ -216,6 +216,24 @@ def test_long_horizon_p200_matches_oracle(setups, pkg, gpu_lib):
     assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
 
 
+@pytest.mark.parametrize("case,p", [("coop-par", 41), ("coop-par", 64), ("ncoop-ser", 90), ("cent-par", 129),
+                                    ("coop-ser", 150), ("cent-ser", 256)])
+def test_other_horizons_match_oracle(case, p, setups, pkg, gpu_lib):
+    """Horizons other than 100/200 run the kernels that read the horizon at run time: shorter and
+    longer power ladders, a partial last giant-step block, both rows-per-thread settings."""
+    s = setups[case]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 3, 160
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 60
+    g = pkg.from_setup(s, batch=B, p=p).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s, p=p).run_closed_loop(x0, be, bo, T, n_threads=3)
+    n = len(x_def)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+
+
 def test_full_size_batch_properties(setups, golden, pkg, gpu_lib):
     """BASELINE configs[3] at full size: 4096 perturbed scenarios, closed loop over the disturbance
     onset.  Size-independent properties: every QP solved, trajectories finite and inside the input
