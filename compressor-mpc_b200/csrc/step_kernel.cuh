@@ -158,7 +158,7 @@ struct SmemLayout {
     // phase 6 aligned and spreads the four column pairs of a DMMA output tile over all banks.
     ldE = kBaby * b_max + 2;
     const int e_size = S::NCH * ldE;
-    const int red_size = S::TPC * (S::NACC | 1);
+    const int red_size = S::WPC * 48;   // exchange buffer of the final reduction
     // E can overwrite its own inputs when every warp can hold its output tiles in registers
     const int n_nt = (b_max * kNC + 7) / 8;
     e_alias = (n_nt + S::WPC - 1) / S::WPC <= kMaxStageTiles / S::NY;
@@ -250,20 +250,41 @@ __device__ __forceinline__ void mma3_shared_b(double (&c)[NT][2], const double (
   }
 }
 
+// v[i] of every lane summed over the warp, for W values at once: each of the log2(W) rounds
+// sends half of the remaining values to the partner lane and keeps the other half, so lane l ends
+// up with the warp total of value l mod W (W - 1 shuffles instead of 5 W).
+template <int W>
+__device__ __forceinline__ double warp_transpose_reduce(double (&v)[W], int lane) {
+  static_assert(W == 32 || W == 16, "value count");
+#pragma unroll
+  for (int h = W / 2; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double keep = up ? v[i + h] : v[i];
+      const double send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  double r = v[0];
+  if (W == 16) r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
+}
+
 // Store a tile into a row-major matrix C (even stride, even column offset) as one 16-byte store
 // per lane.  Rows >= mc and column pairs starting at >= nc_pad are dropped (nc_pad even; a pad
 // column inside the pair receives an exact zero because the B operand's pad column is zero).
 template <bool ADD_EYE = false>
 __device__ __forceinline__ void tile_store(double* C, int ldc, int row_off, int col_off, int mc, int nc_pad,
-                                           int mt, int nt, int lane, const double (&c)[2]) {
+                                           int mt, int nt, int lane, const double (&c)[2], int n_eye = 0) {
   const int r = 8 * mt + (lane >> 2), cc = 8 * nt + 2 * (lane & 3);
   if (r < mc && cc < nc_pad) {
     double2 v;
     v.x = c[0];
     v.y = c[1];
-    if (ADD_EYE) {
-      if (r == cc) v.x += 1.0;
-      if (r == cc + 1) v.y += 1.0;
+    if (ADD_EYE) {   // + I_(n_eye)
+      if (r == cc && r < n_eye) v.x += 1.0;
+      if (r == cc + 1 && r < n_eye) v.y += 1.0;
     }
     *reinterpret_cast<double2*>(C + (row_off + r) * ldc + col_off + cc) = v;
   }
@@ -424,10 +445,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   if (t < 4 * N) cc_v = wk[kWCc + t];
   if (t < 4) yd_v = y[size_t(scen) * 4 + t];
   else if (t < 8) yd_v = gs[kOffDx + N + t - 4];
-  // every matrix slot of the region (powers, L, R, V) is cleared: operands are read zero-padded
-  for (int i = t + 5 * kNNP; i < lay.lr_end - lay.region; i += TPC) scr[i] = 0.0;
-  for (int i = t + kNNP; i < 4 * kNNP; i += TPC) scr[i] = 0.0;
-  if (t < 6 * kLD) U[t] = 0.0;
+  // Zero padding without clearing the region: the hand-over record arrives zero-padded, every
+  // product below stores all kLD rows/columns of its result (a pad row of A or pad column of B gives
+  // an exact zero), and the pads of the three seeds (L, R, V) are cleared where they are planted.
 #pragma unroll
   for (int k = 0; k < NLD; ++k) {
     const int i = t + k * TPC;
@@ -456,26 +476,26 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     frag_b(Ac, kLD, 1, lane, bb[1]);
     frag_b(Xc, kLD, 0, lane, bb[2]);
     mma3_shared_a<3>(cc, a, bb, 2);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0]);
-    tile_store(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1]);
+    tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
+    tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
     group_sync(g, TPC);
     frag_a(A2, kLD, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 2);
-    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0]);
-    tile_store(A3, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1]);
+    tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
+    tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
     group_sync(g, TPC);
     const double Ts = P.Ts;
     const double k1 = Ts, k2 = Ts * Ts / 2.0, k3 = Ts * Ts * Ts / 6.0, k4 = Ts * Ts * Ts * Ts / 24.0;
-    for (int idx = t; idx < N * kLD; idx += TPC) {
+    for (int idx = t; idx < kNNP; idx += TPC) {   // pads included: they come out as exact zeros
       const int i = idx / kLD, j = idx % kLD;
-      if (j < N) Acom[idx] = k1 * (i == j ? 1.0 : 0.0) + k2 * Ac[idx] + k3 * A2[idx] + k4 * A3[idx];
+      Acom[idx] = k1 * ((i == j && i < N) ? 1.0 : 0.0) + k2 * Ac[idx] + k3 * A2[idx] + k4 * A3[idx];
     }
     group_sync(g, TPC);
     // Ad = I + Acom Ac (into the A2 slot), [Bd | fd] = Acom Xc
     frag_a(Acom, kLD, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 3);
-    tile_store<true>(A2, kLD, 0, 0, N, kLD, mt_w, 0, lane, cc[0]);
-    tile_store<true>(A2, kLD, 0, 0, N, kLD, mt_w, 1, lane, cc[1]);
+    tile_store<true>(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0], N);
+    tile_store<true>(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1], N);
     tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
     group_sync(g, TPC);
   }
@@ -494,9 +514,16 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // R_b = Ad^(8b) [Bd fd X40]: blocks [2^j, 2^(j+1)) = Ad^(8*2^j) * blocks [0, 2^j), j = 0..
   // X40 = state reached after the 40 queued delayed inputs have been applied (free response
   // of the delay line): conv[r] = C~ Ad^(r-39) X40 for r >= 39 comes out of the same table.
-  for (int idx = t; idx < NY * N; idx += TPC) L[(idx / N) * kBaby * kLD + idx % N] = Cc[P.c[g].out_idx[idx / N] * N + idx % N];
-  for (int idx = t; idx < N * 5; idx += TPC) R[(idx / 5) * ldr + idx % 5] = BF[(idx / 5) * kNC + idx % 5];
-  for (int idx = t; idx < N * 2; idx += TPC) V[(idx >> 1) * kLDV + (idx & 1)] = BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)];
+  for (int idx = t; idx < NY * kLD; idx += TPC) {
+    const int yy = idx / kLD, j = idx % kLD;
+    L[yy * kBaby * kLD + j] = (j < N) ? Cc[P.c[g].out_idx[yy] * N + j] : 0.0;
+  }
+  for (int idx = t; idx < kLD * 8; idx += TPC) {   // the whole first column tile of R (column 5 = X40 comes later)
+    const int i = idx >> 3, j = idx & 7;
+    R[i * ldr + j] = (i < N && j < 5) ? BF[i * kNC + j] : 0.0;
+  }
+  for (int idx = t; idx < kLD * 2; idx += TPC)
+    V[(idx >> 1) * kLDV + (idx & 1)] = ((idx >> 1) < N) ? BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)] : 0.0;
   group_sync(g, TPC);
   // The stages are unrolled with a compile-time index: every stage but the last one of the run has
   // compile-time tile counts, so its DMMAs are straight-line code with nothing to predicate.
@@ -506,6 +533,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     const double* Pm = Pw + j * kNNP;
     double* Pn = Pw + s * kNNP;
     if constexpr (j == 3) {
+      CMPC_TICK(9);
       // X40 = P(P(P(P U_0 + U_1) + U_2) + U_3) + U_4 with U_b = sum_{a,d} V_(7-a)[:, d] q_d[8b + a],
       // P = Ad^8 = Pm.  Warp 0 of the group, lanes 0..N-1 hold one state each.
       for (int idx = t; idx < 5 * N; idx += TPC) {
@@ -572,7 +600,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
       mma3_shared_a_range<3, 0, 3>(cq, a, bq);
       mma3_shared_b_range<2, n_lm>(cl, al, bl);
-      tile_store(V, kLDV, 0, vc, N, vc, mt_w, 0, lane, cq[2]);
+      tile_store(V, kLDV, 0, vc, kLD, vc, mt_w, 0, lane, cq[2]);
 #pragma unroll
       for (int mt = 0; mt < n_lm; ++mt) {
         const int cc = 8 * mt_w + 2 * (lane & 3);
@@ -583,8 +611,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
           *reinterpret_cast<double2*>(L + (l_row[mt] + l_cnt) * kLD + cc) = v;
         }
       }
-      tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 0, lane, cq[0]);
-      tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 1, lane, cq[1]);
+      tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cq[0]);
+      tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cq[1]);
     } else {
       constexpr int r_base = 1 << (j - 3);
       if (s < n_pow) {
@@ -598,9 +626,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         for (int i = 0; i < n_first; ++i) frag_b(R, ldr, i, lane, bq[2 + i]);
         mma3_shared_a_range<2 + n_first, 0, 2 + n_first>(cq, a, bq);
 #pragma unroll
-        for (int i = 0; i < n_first; ++i) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, i, lane, cq[2 + i]);
-        tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 0, lane, cq[0]);
-        tile_store(Pn, kLD, 0, 0, N, kLD, mt_w, 1, lane, cq[1]);
+        for (int i = 0; i < n_first; ++i) tile_store(R, ldr, 0, r_base * kNC, kLD, r_cols, mt_w, i, lane, cq[2 + i]);
+        tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cq[0]);
+        tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cq[1]);
 #pragma unroll
         for (int nt0 = 4; nt0 < n_rt; nt0 += 4) {
           double bw[4][3], cw[4][2];
@@ -610,7 +638,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
           mma3_shared_a<4>(cw, a, bw, n_rt - nt0 < 4 ? n_rt - nt0 : 4);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt0 + i, lane, cw[i]);
+            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, kLD, r_cols, mt_w, nt0 + i, lane, cw[i]);
         }
       } else {
         // last stage of the run: only the blocks up to b_max, and no further power
@@ -625,7 +653,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
           mma3_shared_a<6>(cw, a, bw, n_rt - nt0 < 6 ? n_rt - nt0 : 6);
 #pragma unroll
           for (int i = 0; i < 6; ++i)
-            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, N, r_cols, mt_w, nt0 + i, lane, cw[i]);
+            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, kLD, r_cols, mt_w, nt0 + i, lane, cw[i]);
         }
       }
     }
@@ -869,21 +897,31 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     }
   }
   CMPC_TICK(6);
-  group_sync(g, TPC);  // E is dead: reuse it as the reduction buffer
+  // Sum the accumulators over the group: a butterfly transpose-reduce in registers leaves the warp
+  // total of accumulator l in lane l (accumulators 32.. in lanes 0..15 of a second pass), then the
+  // warps of the group meet through a few words of shared memory.
   {
-    constexpr int RS = S::NACC | 1;  // odd stride: conflict-free 64-bit stores
-    double* red = E;
+    static_assert(S::NACC <= 48, "accumulator count");
+    constexpr int RS = 48;
+    double lo[32], tot_hi = 0.0;
 #pragma unroll
-    for (int i = 0; i < S::NACC; ++i) red[t * RS + i] = acc[i];
+    for (int i = 0; i < 32; ++i) lo[i] = (i < S::NACC) ? acc[i] : 0.0;
+    const double tot_lo = warp_transpose_reduce<32>(lo, lane);
+    if constexpr (S::NACC > 32) {
+      double hi[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) hi[i] = (32 + i < S::NACC) ? acc[32 + i] : 0.0;
+      tot_hi = warp_transpose_reduce<16>(hi, lane);
+    }
+    group_sync(g, TPC);  // E is dead: reuse it as the exchange buffer
+    double* red = E;
+    red[warp * RS + lane] = tot_lo;
+    if (S::NACC > 32 && lane < 16) red[warp * RS + 32 + lane] = tot_hi;
     group_sync(g, TPC);
     if (t < S::NACC) {
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < TPC; k += 2) {
-        s0 += red[k * RS + t];
-        s1 += red[(k + 1) * RS + t];
-      }
-      const double v = s0 + s1;
+      double v = red[t];
+#pragma unroll
+      for (int w = 1; w < WPC; ++w) v += red[w * RS + t];
       if (t < NH) {
         int a = 0, rem = t;
         while (rem >= NV - a) { rem -= NV - a; ++a; }
