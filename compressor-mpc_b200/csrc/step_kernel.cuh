@@ -536,21 +536,33 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       CMPC_TICK(9);
       // X40 = P(P(P(P U_0 + U_1) + U_2) + U_3) + U_4 with U_b = sum_{a,d} V_(7-a)[:, d] q_d[8b + a],
       // P = Ad^8 = Pm.  Warp 0 of the group, lanes 0..N-1 hold one state each.
-      for (int idx = t; idx < 5 * N; idx += TPC) {
-        const int b = idx / N, i = idx % N;
-        double acc = 0.0;
+      // U (N x 5) = V (N x 16) Qm (16 x 5) on the tensor cores, Qm[2 va + d][b] = q_d[8 b + 7 - va]:
+      // warp w owns row block w, K = 16 is four k-tiles
+      {
+        double cu[2] = {0.0, 0.0};
+        const int n = lane >> 2;
 #pragma unroll
-        for (int a = 0; a < kBaby; ++a) {
-          acc = fma(V[i * kLDV + 2 * (7 - a)], q[8 * b + a], acc);
-          acc = fma(V[i * kLDV + 2 * (7 - a) + 1], q[kDelay + 8 * b + a], acc);
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = 4 * kk + (lane & 3);
+          const int vr = 8 * mt_w + (lane >> 2);   // rows past the matrix only feed rows that are dropped
+          const double av = V[(vr < kLD ? vr : 0) * kLDV + k];
+          const double bv = (n < 5) ? q[(k & 1) * kDelay + 8 * n + 7 - (k >> 1)] : 0.0;
+          dmma_884(cu, av, bv);
         }
-        U[b * kLD + i] = acc;
+        const int i = 8 * mt_w + (lane >> 2), b = 2 * (lane & 3);
+        if (i < kLD) {
+          if (b < 5) U[b * kLD + i] = cu[0];
+          if (b + 1 < 5) U[(b + 1) * kLD + i] = cu[1];
+        }
       }
       group_sync(g, TPC);
       if (warp == 0) {
         // Z_b = state at the start of delay block b (Z_0 = 0) goes to V[:, b]: phase 5 turns it
         // into C~ Ad^a Z_b for the rows that still see a partially drained delay line
         double z = (lane < N) ? U[lane] : 0.0;
+        double pr[N];   // this lane's row of P, reused by every step
+#pragma unroll
+        for (int k = 0; k < N; ++k) pr[k] = Pm[(lane < N ? lane : 0) * kLD + k];
         if (lane < kLD) V[lane * kLDV] = 0.0;
         for (int b = 1; b < 5; ++b) {
           if (lane < kLD) {
@@ -562,8 +574,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
             double a0 = U[b * kLD + lane], a1 = 0.0;
 #pragma unroll
             for (int k = 0; k < N; k += 2) {
-              a0 = fma(Pm[lane * kLD + k], U[5 * kLD + k], a0);
-              if (k + 1 < N) a1 = fma(Pm[lane * kLD + k + 1], U[5 * kLD + k + 1], a1);
+              a0 = fma(pr[k], U[5 * kLD + k], a0);
+              if (k + 1 < N) a1 = fma(pr[k + 1], U[5 * kLD + k + 1], a1);
             }
             z = a0 + a1;
           }
