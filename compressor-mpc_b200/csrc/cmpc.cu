@@ -61,6 +61,7 @@ struct cmpc_handle {
   bool initialized = false;
   bool capture = false;
   bool timing = false;
+  bool lin_ahead = false;   // closed loop: the next record's observer update + linearisation are already done
   std::vector<cudaEvent_t> ev;   // pairs (start, stop) around control-step launches
   size_t ev_used = 0;
 };
@@ -137,6 +138,7 @@ int launch_init(cmpc_handle* h, const double* x, const double* u, const double* 
                 cudaStream_t st) {
   const int B = h->cfg.batch;
   h->P.ring_pos = 0;
+  h->lin_ahead = false;
   init_kernel<S><<<(B + 127) / 128, 128, 0, st>>>(B, h->G, x, u, uf, y, h->P);
   h->launches++;
   CU(cudaGetLastError());
@@ -157,9 +159,13 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
     h->ev_used += 4;
     CU(cudaEventRecord(ev[0], st));
   }
-  // K0: observer + linearisation, 4 threads per (scenario, controller)
-  const int n_thr = B * S::NCTRL * 4;
-  lin_kernel<S><<<(n_thr + 127) / 128, 128, 0, st>>>(h->P, h->G, y);
+  // K0: observer + linearisation, 4 threads per (scenario, controller).  Inside a closed-loop run
+  // the previous record's plant kernel has already done this work (lin_ahead).
+  if (!h->lin_ahead) {
+    const int n_thr = B * S::NCTRL * 4;
+    lin_kernel<S><<<(n_thr + 127) / 128, 128, 0, st>>>(h->P, h->G, y);
+    h->launches++;
+  }
   if (ev) CU(cudaEventRecord(ev[1], st));
   // K1: discretisation, prediction, QP assembly; one CTA per scenario
   assemble_variant<S>(h->cfg.p)<<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
@@ -168,7 +174,7 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
   solve_kernel<S><<<(B * S::NCTRL + 63) / 64, 64, 0, st>>>(h->P, h->G, u);
   h->P.ring_pos = (h->P.ring_pos + 1) % kRing;   // the oldest ring slot was consumed and refilled
   if (ev) CU(cudaEventRecord(ev[3], st));
-  h->launches += 3;
+  h->launches += 2;
   CU(cudaGetLastError());
   return CMPC_OK;
 }
@@ -190,8 +196,9 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
   for (int k = first_step; k < first_step + n_steps; ++k) {
     int rc = launch_step<S>(h, A.y, A.u, st);
     if (rc) return rc;
-    cl_advance_kernel<S::PLANT, S::NCTRL><<<(2 * B + 63) / 64, 64, 0, st>>>(B, k, t, h->cfg.Ts, A, h->G.status,
-                                                                         h->G.active, h->G.objective);
+    // plant side of record k, and the observer update + linearisation of record k + 1
+    cl_advance_kernel<S><<<(8 * B + 63) / 64, 64, 0, st>>>(h->P, h->G, k, t, h->cfg.Ts, A, true);
+    h->lin_ahead = true;
     h->launches++;
     t += h->cfg.Ts;
   }
@@ -477,6 +484,7 @@ int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
 int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_dev, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
+  if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
   if (!y_dev || !u_dev) return fail(CMPC_ERR_ARG, "null argument");
   CMPC_DISPATCH(h->shape, launch_step, h, y_dev, u_dev, static_cast<cudaStream_t>(stream));
 }
@@ -484,6 +492,7 @@ int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_de
 int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
   if (int rc = check_handle(h)) return rc;
   if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
+  if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
   if (!y || !u) return fail(CMPC_ERR_ARG, "null argument");
   const size_t bytes = size_t(h->cfg.batch) * 4 * sizeof(double);
   CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, nullptr));

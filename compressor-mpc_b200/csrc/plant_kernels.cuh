@@ -112,24 +112,66 @@ __device__ bool dopri5_try_step_pair(unsigned full, int c, const double uc[4], d
   xt[5] = xn[5] = 0.0;
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * b21 * k1[i];
-  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k2);
+  {
+    Vec6 xin, dv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
+    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k2[i] = dv.v[i];
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b31 * k1[i] + b32 * k2[i]);
-  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k3);
+  {
+    Vec6 xin, dv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
+    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k3[i] = dv.v[i];
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b41 * k1[i] + b42 * k2[i] + b43 * k3[i]);
-  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k4);
+  {
+    Vec6 xin, dv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
+    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k4[i] = dv.v[i];
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b51 * k1[i] + b52 * k2[i] + b53 * k3[i] + b54 * k4[i]);
-  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k5);
+  {
+    Vec6 xin, dv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
+    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k5[i] = dv.v[i];
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     xt[i] = xs[i] + h * (b61 * k1[i] + b62 * k2[i] + b63 * k3[i] + b64 * k4[i] + b65 * k5[i]);
-  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k6);
+  {
+    Vec6 xin, dv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
+    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k6[i] = dv.v[i];
+  }
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     xn[i] = xs[i] + h * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
-  pair_derivative<PLANT>(full, c, xn, uc, u_tank, k7);
+  {
+    Vec6 xin, dv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xin.v[i] = xn[i];
+    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k7[i] = dv.v[i];
+  }
   // squared scaled errors of this lane's states; summed in plant state order 0..N-1
   double e2[6];
 #pragma unroll
@@ -230,14 +272,11 @@ __global__ void cl_start_kernel(int B, const double* __restrict__ x0, ClosedLoop
 // actuator delay rings, integrate the plant over one sampling interval (one compressor per lane
 // of the pair) and produce the next measurement.
 template <int PLANT, int NCTRL>
-__global__ void __launch_bounds__(64)
-cl_advance_kernel(int B, int k, double t_k, double Ts, ClosedLoopArrays A, const int* __restrict__ status,
-                  const unsigned* __restrict__ active, const double* __restrict__ objective) {
+__device__ __forceinline__ void advance_pair(int b, int c, unsigned pair_mask, int k, double t_k, double Ts,
+                                             const ClosedLoopArrays& A, const int* __restrict__ status,
+                                             const unsigned* __restrict__ active,
+                                             const double* __restrict__ objective, double (&y_next)[4]) {
   constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN, REC = 1 + N + 8;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = tid >> 1, c = tid & 1;
-  if (b >= B) return;
-  const unsigned pair_mask = 3u << (threadIdx.x & 30);
   double u[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) u[i] = A.u[size_t(b) * 4 + i];
@@ -289,8 +328,8 @@ cl_advance_kernel(int B, int k, double t_k, double Ts, ClosedLoopArrays A, const
   const double p2_o = __shfl_xor_sync(pair_mask, p2, 1), sd_o = __shfl_xor_sync(pair_mask, sd, 1);
 #pragma unroll
   for (int i = 0; i < 5; ++i) A.x[size_t(b) * N + 5 * c + i] = xs[i];
+  double y[4] = {0.0, 0.0, 0.0, 0.0};
   if (c == 0) {
-    double y[4];
     if (PLANT == 0) {
       y[0] = sd; y[1] = sd_o; y[2] = p2 - p2_o; y[3] = xs[5];
       A.x[size_t(b) * N + (PLANT == 0 ? 10 : 0)] = xs[5];
@@ -300,6 +339,33 @@ cl_advance_kernel(int B, int k, double t_k, double Ts, ClosedLoopArrays A, const
 #pragma unroll
     for (int i = 0; i < 4; ++i) A.y[size_t(b) * 4 + i] = y[i];
   }
+  // both lanes leave with the measurement (lane 0 of the pair formed it)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y_next[i] = __shfl_sync(pair_mask, y[i], threadIdx.x & 30);
+}
+
+// Plant side of closed-loop record k.  Eight lanes per scenario: lanes 0 and 1 of the octet are the
+// two compressors (record, delay rings, Dormand-Prince over [t_k, t_k + Ts], next measurement);
+// with lin_next all eight then do the observer update and linearisation of record k + 1 (the work
+// of lin_kernel: lane = (sub-controller, part)), so that the next launch of the loop is
+// assemble_kernel again.
+template <class S>
+__global__ void __launch_bounds__(64)
+cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, ClosedLoopArrays A, bool lin_next) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = tid >> 3, o = tid & 7;
+  const bool on = b < P.batch;
+  const int base = threadIdx.x & 24;   // first lane of the octet inside its warp
+  double y[4] = {0.0, 0.0, 0.0, 0.0};
+  if (on && o < 2) advance_pair<S::PLANT, S::NCTRL>(b, o, 3u << base, k, t_k, Ts, A, G.status, G.active, G.objective, y);
+  if (!lin_next) return;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = __shfl_sync(0xffffffffu, y[i], base);
+  const int g = o >> 2, part = o & 3;
+  const bool lin_on = on && g < S::NCTRL;
+  const unsigned m = __ballot_sync(0xffffffffu, lin_on);
+  if (lin_on) lin_part<S>(P, G, b, g, part, y, m);
 }
 
 // NerveCenter::Initialize + DistributedController::Initialize (nerve_center.h:98-104,186-203,

@@ -322,7 +322,7 @@ __device__ __forceinline__ double plant_c_row_dot(const double* x, int r, const 
 // of the continuous-time matrices in the hand-over record (whose zero pattern never changes).
 template <class S>
 __device__ __forceinline__ void lin_part(const StepParams& P, const DeviceState& G, int scen, int g, int part,
-                                         const double (&yv)[4]) {
+                                         const double (&yv)[4], unsigned sync_mask) {
   constexpr int N = S::N, NOBS = S::NOBS, NIN = S::NIN;
   double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   const double* ss = G.scen + size_t(scen) * kScenStateStride;
@@ -344,6 +344,7 @@ __device__ __forceinline__ void lin_part(const StepParams& P, const DeviceState&
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) xh[i] += dx[i];
+  __syncwarp(sync_mask);   // every part has read the old observer state before part 3 replaces it
   if (part == 3) {
 #pragma unroll
     for (int i = 0; i < N; ++i) gs[kOffXhat + i] = xh[i];
@@ -370,11 +371,13 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int part = tid & 3, quad = tid >> 2;
   const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
-  if (scen >= P.batch) return;
+  const bool on = scen < P.batch;
+  const unsigned m = __ballot_sync(0xffffffffu, on);
+  if (!on) return;
   double yv[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) yv[r] = y[size_t(scen) * 4 + r];
-  lin_part<S>(P, G, scen, g, part, yv);
+  lin_part<S>(P, G, scen, g, part, yv, m);
 }
 
 #ifdef CMPC_PHASE_TIMING
@@ -400,6 +403,16 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   if (scen >= P.batch) return;
   const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
   const int lane = t & 31, warp = t >> 5;
+#ifdef CMPC_POISON_SMEM
+  // test builds: start from NaN-filled shared memory, so that any read of a word this launch did
+  // not write shows up in the parity tests
+  {
+    unsigned dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    for (unsigned i = threadIdx.x; i < dyn_bytes / 8; i += blockDim.x) smem[i] = __longlong_as_double(0x7ff8dead0000beefLL);
+    __syncthreads();
+  }
+#endif
   constexpr bool CT = PCT > 0;
   constexpr int kBmaxCt = (PCT + kBaby - 1) / kBaby;
   const int p = CT ? PCT : P.p, b_max = CT ? kBmaxCt : P.b_max;
@@ -1057,7 +1070,7 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     if (wset == kQpNoGuess) wset = 0;     // no warm start: begin from the unconstrained minimiser
     const bool pd = qt_inverse(J);
     QtReduced red;
-    bool red_ok = qt_prepare(J, bnd, wset, red) && pd;
+    bool red_ok = false, need_prep = true;   // red belongs to wset once prepared
     double x[4] = {0.0, 0.0, 0.0, 0.0}, lam[4] = {0.0, 0.0, 0.0, 0.0}, fi[4] = {0.0, 0.0, 0.0, 0.0};
     int status = pd ? 0 : 3;
     for (int it = 0; it < P.n_iter; ++it) {
@@ -1071,31 +1084,47 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
         for (int k = 0; k < 4; ++k) s = fma(Gx[i][k], zo[k], s);
         fi[i] = s;
       }
-      bool ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
-      // the working set changes: repair it one constraint at a time in registers (each accepted
-      // result satisfies the KKT conditions of the full QP, i.e. is the unique minimiser) ...
-      for (int rep = 0; rep < 6 && pd && !ok && red_ok; ++rep) {
-        const unsigned nw = qt_repair(red, x, lam, bnd, wset);
-        if (nw == wset) break;
-        wset = nw;
-        red_ok = qt_prepare(J, bnd, wset, red);
-        ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
-      }
-      if (pd && !ok) {
-        // ... and only if that does not settle, the general dual active-set solve
-        QpBounds4 qb;
-        qb.lo0 = bnd[0]; qb.lo1 = bnd[1]; qb.up0 = -bnd[4]; qb.up1 = -bnd[5];
-        qb.rlo0 = bnd[8]; qb.rlo1 = bnd[9]; qb.rup0 = -bnd[12]; qb.rup1 = -bnd[13];
-        unsigned new_w = wset;
-        status = qp_fallback4(gH, fi[0], fi[1], fi[2], fi[3], qb, &new_w);
-        if (status == 0) {
+      // One copy of prepare / evaluate / repair (they are large, fully unrolled register code and
+      // this kernel is bound by instruction fetch).  The warm-start working set is evaluated first;
+      // when it is not optimal it is repaired one constraint at a time in registers (each accepted
+      // result satisfies the KKT conditions of the full QP, i.e. is the unique minimiser), and
+      // only if that does not settle, the general dual active-set solve supplies the set.
+      if (pd) {
+        bool fell_back = false;
+        int n_rep = 0;
+        for (;;) {
+          if (need_prep) {
+            red_ok = qt_prepare(J, bnd, wset, red);
+            need_prep = false;
+          }
+          const bool ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
+          if (ok) {
+            status = 0;
+            break;
+          }
+          if (fell_back) {
+            status = 1;   // should not happen: KKT of the set the general solver returned
+            break;
+          }
+          if (red_ok && n_rep < 6) {
+            const unsigned nw = qt_repair(red, x, lam, bnd, wset);
+            ++n_rep;
+            if (nw != wset) {
+              wset = nw;
+              need_prep = true;
+              continue;
+            }
+          }
+          QpBounds4 qb;
+          qb.lo0 = bnd[0]; qb.lo1 = bnd[1]; qb.up0 = -bnd[4]; qb.up1 = -bnd[5];
+          qb.rlo0 = bnd[8]; qb.rlo1 = bnd[9]; qb.rup0 = -bnd[12]; qb.rup1 = -bnd[13];
+          unsigned new_w = wset;
+          status = qp_fallback4(gH, fi[0], fi[1], fi[2], fi[3], qb, &new_w);
+          fell_back = true;
+          if (status != 0) break;
           wset = new_w;
-          red_ok = qt_prepare(J, bnd, wset, red);
-          ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;
-          if (!ok) status = 1;   // should not happen: KKT of the new set
+          need_prep = true;
         }
-      } else if (pd) {
-        status = 0;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) z[k] = (status == 0) ? x[k] : 0.0;   // mpc_qp_solver.cc:66-69: zeros on failure

@@ -234,6 +234,21 @@ def test_other_horizons_match_oracle(case, p, setups, pkg, gpu_lib):
     assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
 
 
+def test_no_launch_reads_uninitialised_shared_memory(pkg, gpu_lib):
+    """The assemble kernel does not clear its operand region: zero padding comes from stored
+    results.  The test build fills shared memory with NaNs at the start of every launch; parity
+    must still hold (tests/poison_check.py, run in a fresh process because the library is chosen at
+    import time)."""
+    import os, pathlib, subprocess, sys
+    root = pathlib.Path(__file__).resolve().parent.parent
+    lib = root / "compressor-mpc_b200" / "libcmpc_b200_poison.so"
+    assert lib.exists(), "libcmpc_b200_poison.so is missing: run __graft_entry__.build()"
+    env = dict(os.environ, CMPC_B200_LIB=str(lib))
+    out = subprocess.run([sys.executable, str(root / "tests" / "poison_check.py")], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_full_size_batch_properties(setups, golden, pkg, gpu_lib):
     """BASELINE configs[3] at full size: 4096 perturbed scenarios, closed loop over the disturbance
     onset.  Size-independent properties: every QP solved, trajectories finite and inside the input
