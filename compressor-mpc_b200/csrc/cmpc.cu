@@ -99,6 +99,23 @@ int find_shape(const cmpc_config& c) {
   return -1;
 }
 
+// Launch with programmatic stream serialisation (see pdl_wait / pdl_trigger in step_kernel.cuh).
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // The assemble_kernel instantiation for a prediction horizon: compile-time horizons for the
 // reference's p = 100 and the 2x sweep, run-time horizon otherwise.
 using AssembleFn = void (*)(StepParams, DeviceState, const double*);
@@ -163,15 +180,15 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
   // the previous record's plant kernel has already done this work (lin_ahead).
   if (!h->lin_ahead) {
     const int n_thr = B * S::NCTRL * 4;
-    lin_kernel<S><<<(n_thr + 127) / 128, 128, 0, st>>>(h->P, h->G, y);
+    CU(launch_pdl(lin_kernel<S>, (n_thr + 127) / 128, 128, 0, st, h->P, h->G, y));
     h->launches++;
   }
   if (ev) CU(cudaEventRecord(ev[1], st));
   // K1: discretisation, prediction, QP assembly; one CTA per scenario
-  assemble_variant<S>(h->cfg.p)<<<B, S::NCTRL * S::TPC, h->smem_bytes, st>>>(h->P, h->G, y);
+  CU(launch_pdl(assemble_variant<S>(h->cfg.p), B, S::NCTRL * S::TPC, h->smem_bytes, st, h->P, h->G, y));
   if (ev) CU(cudaEventRecord(ev[2], st));
   // K2: Jacobi sweeps + update; one warp per scenario
-  solve_kernel<S><<<(B * S::NCTRL + 63) / 64, 64, 0, st>>>(h->P, h->G, u);
+  CU(launch_pdl(solve_kernel<S>, (B * S::NCTRL + 63) / 64, 64, 0, st, h->P, h->G, u));
   h->P.ring_pos = (h->P.ring_pos + 1) % kRing;   // the oldest ring slot was consumed and refilled
   if (ev) CU(cudaEventRecord(ev[3], st));
   h->launches += 2;
@@ -197,7 +214,7 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
     int rc = launch_step<S>(h, A.y, A.u, st);
     if (rc) return rc;
     // plant side of record k, and the observer update + linearisation of record k + 1
-    cl_advance_kernel<S><<<(8 * B + 63) / 64, 64, 0, st>>>(h->P, h->G, k, t, h->cfg.Ts, A, true);
+    CU(launch_pdl(cl_advance_kernel<S>, (8 * B + 63) / 64, 64, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
     h->lin_ahead = true;
     h->launches++;
     t += h->cfg.Ts;

@@ -352,6 +352,8 @@ __device__ __forceinline__ void advance_pair(int b, int c, unsigned pair_mask, i
 template <class S>
 __global__ void __launch_bounds__(64)
 cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, ClosedLoopArrays A, bool lin_next) {
+  pdl_wait();
+  pdl_trigger();   // single wave
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = tid >> 3, o = tid & 7;
   const bool on = b < P.batch;

@@ -112,6 +112,13 @@ struct DeviceState {
   long long* ticks;    // [B][16] per-phase clock64() stamps (CMPC_PHASE_TIMING builds only)
 };
 
+// Programmatic dependent launch: the kernels of a step are launched with programmatic stream
+// serialisation, so the next kernel's CTAs may become resident while this grid drains.  pdl_wait()
+// (first statement of every kernel) blocks until the preceding grid has completed and its writes are
+// visible; pdl_trigger() tells the scheduler that this CTA no longer minds company.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
@@ -368,6 +375,8 @@ __device__ __forceinline__ void lin_part(const StepParams& P, const DeviceState&
 template <class S>
 __global__ void __launch_bounds__(128)
 lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();   // single wave: the next grid may queue up behind it at once
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int part = tid & 3, quad = tid >> 2;
   const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
@@ -394,6 +403,7 @@ template <class S, int RPT, int PCT>
 __global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
 assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
+  pdl_wait();
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
   constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NSC = S::NSC, NH = S::NH;
 #ifdef CMPC_PHASE_TIMING
@@ -922,6 +932,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     }
   }
   CMPC_TICK(6);
+  pdl_trigger();   // only the reduction is left: once the last wave is here, the solve grid may move in
   // Sum the accumulators over the group: a butterfly transpose-reduce in registers leaves the warp
   // total of accumulator l in lane l (accumulators 32.. in lanes 0..15 of a second pass), then the
   // warps of the group meet through a few words of shared memory.
@@ -1033,6 +1044,8 @@ __device__ __forceinline__ void apriori_update(const StepParams& P, const Device
 template <class S>
 __global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
 solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+  pdl_wait();
+  pdl_trigger();   // single wave
   constexpr int NU = S::NU, NV = S::NV, NVO = S::NVO, NCTRL = S::NCTRL;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (NV == 4 && NCTRL == 2) {
