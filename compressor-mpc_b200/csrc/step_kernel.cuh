@@ -5,7 +5,9 @@
 //   assemble_kernel  discretisation, prediction and QP assembly: small dense matrix algebra on the
 //                    FP64 tensor cores, one CTA per scenario, one thread group per sub-controller
 //   solve_kernel     Jacobi sweeps of the QP solves, first move, a-priori observer update: one
-//                    warp per scenario (16 lanes per sub-controller)
+//                    lane pair per scenario (lane = sub-controller), the QP in registers
+// In the closed loop (plant_kernels.cuh) the plant kernel that follows also does lin_kernel's work
+// for the next record, and all kernels are chained by programmatic dependent launch.
 //
 // Reference path replaced: NerveCenter::GetNextInputWithTiming
 // (include/nerve_center.h:134-182) -> DistributedController::GenerateInitialQP

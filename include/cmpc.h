@@ -89,7 +89,10 @@ int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
 
 /* ControllerInterface::GetNextInput / NerveCenter::GetNextInputWithTiming
  * (controller_interface.h:46, nerve_center.h:125-182), batched: y B x 4 -> u B x 4.
- * Host buffers; H2D of y and D2H of u happen inside. */
+ * Host buffers; H2D of y and D2H of u happen inside.
+ * CMPC_ERR_STATE after a closed-loop run on the same handle (cmpc_run_closed_loop*): that loop
+ * has already consumed the next measurement (its plant kernel runs the observer update and the
+ * linearisation of the following record), so the handle needs cmpc_initialize first. */
 int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u);
 /* Same with device-resident y/u (B x 4 doubles each) on `stream` (a cudaStream_t), no sync. */
 int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_dev, void* stream);
@@ -120,8 +123,9 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
                                 const double* block_off_dev, double* traj_dev,
                                 uint32_t* qp_active_dev, double* qp_objective_dev,
                                 int32_t* qp_status_dev, void* stream);
-/* Per-kernel device timing: when on, every control step (its three kernels: linearise, assemble,
- * solve) is bracketed by CUDA events on its stream; cmpc_get_timing synchronises, returns the
+/* Per-kernel device timing: when on, every control step (linearise [host-facing step only],
+ * assemble, solve) is bracketed by CUDA events on its stream (which also keeps its kernels from
+ * overlapping by dependent launch: use it to explain a run, not to time one); cmpc_get_timing synchronises, returns the
  * number of timed control steps, the summed duration of whole control steps and of their
  * assemble kernels alone, and resets the counters. */
 int cmpc_set_timing(cmpc_handle* h, int on);
