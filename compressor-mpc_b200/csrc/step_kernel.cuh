@@ -159,20 +159,22 @@ struct SmemLayout {
     cz = take(kDelay * S::NY);
     region = o;
     const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then Ad^(2^j)
-    L = region + n_scr;
-    R = L + kBaby * S::NY * kLD;
-    V = R + kLD * giant_stride(b_max);      // 12 rows: rows >= N stay zero (K padding)
-    lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
     // E is channel-major: E[(y kNC + c) ldE + r].  ldE = 2 mod 4 keeps the 16-byte row-pair loads of
     // phase 6 aligned and spreads the four column pairs of a DMMA output tile over all banks.
     ldE = kBaby * b_max + 2;
-    const int e_size = S::NCH * ldE;
+    const int e_size = (S::NCH * ldE + 1) & ~1;
     const int red_size = S::WPC * 48;   // exchange buffer of the final reduction
-    // E can overwrite its own inputs when every warp can hold its output tiles in registers
+    // E always starts where the (by then dead) powers are.  It can also overwrite its own inputs
+    // L, R, V when every warp can hold its output tiles in registers; for longer horizons L, R, V
+    // are placed behind it.
     const int n_nt = (b_max * kNC + 7) / 8;
     e_alias = (n_nt + S::WPC - 1) / S::WPC <= kMaxStageTiles / S::NY;
-    E = e_alias ? region : lr_end;
-    int end = e_alias ? (lr_end > region + e_size ? lr_end : region + e_size) : lr_end + e_size;
+    E = region;
+    L = region + ((e_alias || n_scr > e_size) ? n_scr : e_size);
+    R = L + kBaby * S::NY * kLD;
+    V = R + kLD * giant_stride(b_max);      // 12 rows: rows >= N stay zero (K padding)
+    lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
+    int end = lr_end > region + e_size ? lr_end : region + e_size;
     if (end < E + red_size) end = E + red_size;
     total = (end + 1) & ~1;
   }
