@@ -235,13 +235,15 @@ def main():
     y0 = y_seq[0].numpy()
     nc.Initialize(x0, np.zeros(4), u_def, y0)
     e2e_s, max_du = 0.0, 0.0
+    y_ptrs = [y_seq[k].data_ptr() for k in range(W + K)]   # pinned host rows; no tensor indexing in the timed region
+    u_ptr = u_host.data_ptr()
     barrier()
     for k in range(W + K):
         if k >= W:
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-        nc.GetNextInputRaw(y_seq[k].data_ptr(), u_host.data_ptr())
+        nc.GetNextInputRaw(y_ptrs[k], u_ptr)   # H2D of y, the three kernels, D2H of u, sync
         if k >= W:
             e2e_s += time.perf_counter() - t0
             max_du = max(max_du, float((u_host - u_seq[k]).abs().max()))
