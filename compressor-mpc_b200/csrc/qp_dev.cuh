@@ -321,86 +321,4 @@ __device__ __noinline__ int qp_solve(const QpData<NV>& P, const double* H, const
   return 0;
 }
 
-// ---- fast path for repeated solves with the same H and working set ----------------------
-// With H and the working set W fixed, the equality-constrained minimiser and its multipliers
-// are affine in f:   x = c - P f,   lambda = lam0 + Lam f
-//   P = J - J N' S^-1 N J,  c = J N' S^-1 b_W,  Lam = S^-1 N J,  lam0 = S^-1 b_W,  S = N J N'.
-// The Jacobi sweeps of one control step change only f (distributed_solver.h:109-115), so these
-// are built once per step and every sweep costs two small mat-vecs plus the KKT check.
-// Layout in shared memory (doubles): P NV*NV | c NV | Lam NV*NV | lam0 NV.
-template <int NV>
-struct QpFastLayout {
-  static constexpr int P = 0, c = NV * NV, Lam = NV * NV + NV, lam0 = 2 * NV * NV + NV, size = 2 * NV * NV + 2 * NV;
-};
-
-template <int NV, int NU>
-__device__ __noinline__ bool qp_prepare(const QpData<NV>& Pd, unsigned wset, double* fast, int* q_out) {
-  using LY = QpFastLayout<NV>;
-  QpWorkingSet<NV> W;
-  W.q = 0;
-  for (int j = 0; j < 4 * NV && W.q < NV; ++j)
-    if ((wset >> j) & 1u) W.idx[W.q++] = j;
-  qp_build_ws<NV, NU>(Pd, W);
-  const int q = W.q;
-  double Sinv[NV][NV];
-  for (int e = 0; e < q; ++e) {
-    double rhs[NV], col[NV];
-    for (int w = 0; w < q; ++w) rhs[w] = (w == e) ? 1.0 : 0.0;
-    if (!qp_solve_spd<NV>(q, W.S, rhs, col)) return false;
-    for (int w = 0; w < q; ++w) Sinv[w][e] = col[w];
-  }
-  for (int w = 0; w < NV; ++w) {
-    double l0 = 0.0;
-    for (int e = 0; e < q; ++e) l0 += (w < q) ? Sinv[w][e] * W.b[e] : 0.0;
-    fast[LY::lam0 + w] = l0;
-    for (int k = 0; k < NV; ++k) {
-      double s = 0.0;
-      for (int e = 0; e < q; ++e) s += (w < q) ? Sinv[w][e] * W.JN[e][k] : 0.0;
-      fast[LY::Lam + w * NV + k] = s;
-    }
-  }
-  for (int k = 0; k < NV; ++k) {
-    double ck = 0.0;
-    for (int w = 0; w < q; ++w) ck += W.JN[w][k] * fast[LY::lam0 + w];
-    fast[LY::c + k] = ck;
-    for (int l = 0; l < NV; ++l) {
-      double s = Pd.J[k][l];
-      for (int w = 0; w < q; ++w) s -= W.JN[w][k] * fast[LY::Lam + w * NV + l];
-      fast[LY::P + k * NV + l] = s;
-    }
-  }
-  *q_out = q;
-  return true;
-}
-
-// One sweep on the fast path: returns true when (x, lambda) satisfies the KKT conditions of
-// the full QP, i.e. W is still the optimal working set.  lam: multipliers of W's members.
-template <int NV, int NU>
-__device__ __forceinline__ bool qp_eval_fast(const QpData<NV>& Pd, const double* fast, int q, unsigned wset,
-                                             const double* f, double* x, double* lam) {
-  using LY = QpFastLayout<NV>;
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double s = fast[LY::c + k];
-#pragma unroll
-    for (int l = 0; l < NV; ++l) s = fma(-fast[LY::P + k * NV + l], f[l], s);
-    x[k] = s;
-  }
-#pragma unroll
-  for (int w = 0; w < NV; ++w) {
-    double s = fast[LY::lam0 + w];
-#pragma unroll
-    for (int l = 0; l < NV; ++l) s = fma(fast[LY::Lam + w * NV + l], f[l], s);
-    lam[w] = s;
-    if (w < q && !(s >= 0.0)) ok = false;
-  }
-#pragma unroll
-  for (int j = 0; j < 4 * NV; ++j) {
-    const bool in_w = (wset >> j) & 1u;
-    if (!in_w && qp_slack<NV, NU>(Pd, j, x) < -kQpPrimalTol) ok = false;
-  }
-  return ok;
-}
-
 }  // namespace cmpc

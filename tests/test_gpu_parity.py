@@ -234,6 +234,38 @@ def test_other_horizons_match_oracle(case, p, setups, pkg, gpu_lib):
     assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
 
 
+def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
+    """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
+    the records are bit-identical to a single call.  A closed-loop run leaves the controller
+    half a step ahead (its plant kernel has already linearised the next record), so the
+    host-facing step refuses to run until the handle is initialised again."""
+    import torch
+    s = setups["coop-par"]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    B, T = 5, 90
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 30
+    ref = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    nc = pkg.from_setup(s, batch=B)
+    dev = torch.device("cuda", 0)
+    d_x0, d_be, d_bo = (torch.from_numpy(a).to(dev) for a in (x0, be, bo))
+    rec = 1 + len(x_def) + 8
+    d_traj = torch.zeros((B, T, rec), dtype=torch.float64, device=dev)
+    d_act = torch.zeros((B, T, 2), dtype=torch.int32, device=dev)
+    for first, count in ((0, 25), (25, 1), (26, 1), (27, T - 27)):
+        nc.run_closed_loop_device(first, count, T, d_x0.data_ptr(), be.shape[1], d_be.data_ptr(), d_bo.data_ptr(),
+                                  d_traj.data_ptr(), d_act.data_ptr(), 0, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_traj.cpu().numpy(), ref["traj"])
+    assert np.array_equal(d_act.cpu().numpy().astype(np.uint32), ref["active"])
+    y0 = np.tile(ol.plant_output(s.plant, x_def), (B, 1))
+    with pytest.raises(pkg.capi.CmpcError, match="cmpc_initialize"):
+        nc.GetNextInput(y0)
+    nc.Initialize(np.tile(x_def, (B, 1)), np.zeros(4), u_def, y0)
+    u = nc.GetNextInput(y0)
+    assert np.isfinite(u).all()
+
+
 def test_no_launch_reads_uninitialised_shared_memory(pkg, gpu_lib):
     """The assemble kernel does not clear its operand region: zero padding comes from stored
     results.  The test build fills shared memory with NaNs at the start of every launch; parity
