@@ -214,13 +214,22 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
     int rc = launch_step<S>(h, A.y, A.u, st);
     if (rc) return rc;
     // plant side of record k, and the observer update + linearisation of record k + 1
-    CU(launch_pdl(cl_advance_kernel<S>, (8 * B + 63) / 64, 64, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
+    CU(launch_pdl(cl_advance_kernel<S>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
     h->lin_ahead = true;
     h->launches++;
     t += h->cfg.Ts;
   }
   CU(cudaGetLastError());
   return CMPC_OK;
+}
+
+// StepParams::obs_states_free: do the observer gains leave the plant-state estimates alone?
+void update_obs_states_free(cmpc_handle* h) {
+  bool free_ = true;
+  for (int c = 0; c < h->NCTRL; ++c)
+    for (int i = 0; i < h->N * 4; ++i)
+      if (h->P.c[c].M[i] != 0.0) free_ = false;
+  h->P.obs_states_free = free_ ? 1 : 0;
 }
 
 int check_handle(cmpc_handle* h) {
@@ -355,6 +364,7 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
     for (int i = 0; i < nu; ++i) cp.R[i * nu + i] = 1.0;
     for (int i = 0; i < 4; ++i) cp.M[(N + i) * 4 + i] = 1.0;  // default gain [0; I]
   }
+  update_obs_states_free(h);
   DeviceState& G = h->G;
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
@@ -461,6 +471,7 @@ int cmpc_set_observer_gain(cmpc_handle* h, int ctrl, const double* M) {
   if (int rc = check_handle(h)) return rc;
   if (ctrl < 0 || ctrl >= h->NCTRL || !M) return fail(CMPC_ERR_ARG, "bad argument");
   std::memcpy(h->P.c[ctrl].M, M, sizeof(double) * (h->N + kNDist) * 4);
+  update_obs_states_free(h);
   return CMPC_OK;
 }
 

@@ -344,30 +344,63 @@ __device__ __forceinline__ void advance_pair(int b, int c, unsigned pair_mask, i
   for (int i = 0; i < 4; ++i) y_next[i] = __shfl_sync(pair_mask, y[i], threadIdx.x & 30);
 }
 
-// Plant side of closed-loop record k.  Eight lanes per scenario: lanes 0 and 1 of the octet are the
-// two compressors (record, delay rings, Dormand-Prince over [t_k, t_k + Ts], next measurement);
-// with lin_next all eight then do the observer update and linearisation of record k + 1 (the work
-// of lin_kernel: lane = (sub-controller, part)), so that the next launch of the loop is
-// assemble_kernel again.
+// Plant side of closed-loop record k, 16 scenarios per 128-thread block.  Warp 0: one lane pair per
+// scenario, lane = compressor (record, delay rings, Dormand-Prince over [t_k, t_k + Ts], next
+// measurement).  With lin_next the block also does lin_kernel's work for record k + 1, so that the
+// next launch of the loop is assemble_kernel again: warps 1-3 fill the linearisation parts, one
+// (scenario, sub-controller, part) per lane -- at the same time as the integration when the
+// observer gain leaves the state estimate alone (P.obs_states_free: the linearisation point then
+// does not depend on the measurement being produced), after it otherwise -- and finally warp 0
+// stores the observer state with the new measurement.
 template <class S>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, ClosedLoopArrays A, bool lin_next) {
   pdl_wait();
   pdl_trigger();   // single wave
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = tid >> 3, o = tid & 7;
-  const bool on = b < P.batch;
-  const int base = threadIdx.x & 24;   // first lane of the octet inside its warp
-  double y[4] = {0.0, 0.0, 0.0, 0.0};
-  if (on && o < 2) advance_pair<S::PLANT, S::NCTRL>(b, o, 3u << base, k, t_k, Ts, A, G.status, G.active, G.objective, y);
-  if (!lin_next) return;
-  __syncwarp();
+  constexpr int kScen = 16, kItems = kScen * S::NCTRL * 3;
+  __shared__ double y_sh[kScen][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.x * kScen;
+  const bool early = lin_next && P.obs_states_free;
+  auto lin_items = [&](bool with_y) {
+    for (int idx = (warp - 1) * 32 + lane; idx < kItems; idx += 96) {
+      const int sl = idx / (3 * S::NCTRL), rem = idx % (3 * S::NCTRL);
+      const int b = b0 + sl;
+      if (b >= P.batch) continue;
+      double y[4] = {0.0, 0.0, 0.0, 0.0};   // not used by the state estimate when obs_states_free
+      if (with_y) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) y[i] = __shfl_sync(0xffffffffu, y[i], base);
-  const int g = o >> 2, part = o & 3;
-  const bool lin_on = on && g < S::NCTRL;
-  const unsigned m = __ballot_sync(0xffffffffu, lin_on);
-  if (lin_on) lin_part<S>(P, G, b, g, part, y, m);
+        for (int i = 0; i < 4; ++i) y[i] = y_sh[sl][i];
+      }
+      lin_part<S>(P, G, b, rem / 3, rem % 3, y, 0u);
+    }
+  };
+  if (warp == 0) {
+    const int b = b0 + (lane >> 1), c = lane & 1;
+    if (b < P.batch) {
+      double y[4];
+      advance_pair<S::PLANT, S::NCTRL>(b, c, 3u << (lane & 30), k, t_k, Ts, A, G.status, G.active, G.objective, y);
+      if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y_sh[lane >> 1][i] = y[i];
+      }
+    }
+  } else if (early) {
+    lin_items(false);
+  }
+  if (!lin_next) return;
+  __syncthreads();
+  if (warp != 0 && !early) lin_items(true);
+  __syncthreads();   // every part has read the old observer state
+  if (warp == 0 && lane < kScen * S::NCTRL) {
+    const int sl = lane / S::NCTRL, b = b0 + sl;
+    if (b < P.batch) {
+      double y[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = y_sh[sl][i];
+      lin_part<S>(P, G, b, lane % S::NCTRL, 3, y, 0u);
+    }
+  }
 }
 
 // NerveCenter::Initialize + DistributedController::Initialize (nerve_center.h:98-104,186-203,

@@ -90,6 +90,9 @@ struct CtrlParams {
 struct StepParams {
   int p, b_max, n_pow, n_iter, batch, ldr;
   int ring_pos;   // position of the oldest entry in the 39-slot delay rings (same for all scenarios)
+  int obs_states_free;   // 1: no observer gain row of a plant state is non-zero (the reference's M = [0; I]),
+                         //    so the a-posteriori state estimate, and with it the linearisation point, does
+                         //    not depend on the new measurement
   double Ts;
   const double* yref;   // [NCTRL][p][NY]
   CtrlParams c[2];
@@ -355,7 +358,8 @@ __device__ __forceinline__ void lin_part(const StepParams& P, const DeviceState&
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) xh[i] += dx[i];
-  __syncwarp(sync_mask);   // every part has read the old observer state before part 3 replaces it
+  if (sync_mask) __syncwarp(sync_mask);   // every part has read the old observer state before part 3 replaces it
+                                          // (0: the caller orders them with a block barrier)
   if (part == 3) {
 #pragma unroll
     for (int i = 0; i < N; ++i) gs[kOffXhat + i] = xh[i];

@@ -234,6 +234,36 @@ def test_other_horizons_match_oracle(case, p, setups, pkg, gpu_lib):
     assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
 
 
+@pytest.mark.parametrize("case", ["coop-par", "cent-ser"])
+def test_custom_observer_gain_matches_oracle(case, setups, pkg, gpu_lib):
+    """A gain with non-zero plant-state rows: the a-posteriori estimate then depends on the new
+    measurement, so the closed loop must linearise after the plant step (with the reference's
+    M = [0; I] it linearises next to it)."""
+    s = setups[case]
+    x_def, _ = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 4, 200
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 40
+    rng = np.random.default_rng(11)
+    nc = pkg.from_setup(s, batch=B)
+    o = ol.Oracle(s)
+    for c in range(nc.n_controllers):
+        M = np.zeros((n + 4, 4))
+        M[n:, :] = np.eye(4) * 0.8
+        M[:n, :] = 2e-3 * rng.standard_normal((n, 4)) * np.abs(x_def)[:, None]
+        nc.SetObserverGain(c, M)
+        o.set_observer_gain(c, M)
+    g = nc.run_closed_loop(x0, be, bo, T)
+    r = o.run_closed_loop(x0, be, bo, T, n_threads=4)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], r["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert rel_err(g["traj"][:, :, 1:1 + n], r["traj"][:, :, 1:1 + n], 1e-3) < 1e-8
+    assert np.array_equal(g["active"], r["active"])
+    # and it is a different controller from the default one
+    d = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    assert np.abs(d["traj"][:, :, 1 + n:5 + n] - g["traj"][:, :, 1 + n:5 + n]).max() > 1e-6
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
