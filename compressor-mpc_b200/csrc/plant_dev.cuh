@@ -383,19 +383,4 @@ __device__ __forceinline__ void pair_derivative(unsigned full, int c, const doub
   }
 }
 
-// The same as an out-of-line call with everything passed by value: the Dormand-Prince stages call
-// it six times per step, and the closed-loop plant kernel is bound by instruction fetch, not by
-// the call overhead.
-struct Vec6 {
-  double v[6];
-};
-template <int PLANT>
-__device__ __noinline__ Vec6 pair_derivative_call(unsigned full, int c, Vec6 x, double u0, double u1, double u2,
-                                                  double u3, double u_tank) {
-  const double uc[4] = {u0, u1, u2, u3};
-  Vec6 d;
-  pair_derivative<PLANT>(full, c, x.v, uc, u_tank, d.v);
-  return d;
-}
-
 }  // namespace cmpc

@@ -112,66 +112,24 @@ __device__ bool dopri5_try_step_pair(unsigned full, int c, const double uc[4], d
   xt[5] = xn[5] = 0.0;
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * b21 * k1[i];
-  {
-    Vec6 xin, dv;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
-    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) k2[i] = dv.v[i];
-  }
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k2);
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b31 * k1[i] + b32 * k2[i]);
-  {
-    Vec6 xin, dv;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
-    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) k3[i] = dv.v[i];
-  }
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k3);
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b41 * k1[i] + b42 * k2[i] + b43 * k3[i]);
-  {
-    Vec6 xin, dv;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
-    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) k4[i] = dv.v[i];
-  }
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k4);
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b51 * k1[i] + b52 * k2[i] + b53 * k3[i] + b54 * k4[i]);
-  {
-    Vec6 xin, dv;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
-    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) k5[i] = dv.v[i];
-  }
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k5);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     xt[i] = xs[i] + h * (b61 * k1[i] + b62 * k2[i] + b63 * k3[i] + b64 * k4[i] + b65 * k5[i]);
-  {
-    Vec6 xin, dv;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xin.v[i] = xt[i];
-    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) k6[i] = dv.v[i];
-  }
+  pair_derivative<PLANT>(full, c, xt, uc, u_tank, k6);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     xn[i] = xs[i] + h * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
-  {
-    Vec6 xin, dv;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xin.v[i] = xn[i];
-    dv = pair_derivative_call<PLANT>(full, c, xin, uc[0], uc[1], uc[2], uc[3], u_tank);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) k7[i] = dv.v[i];
-  }
+  pair_derivative<PLANT>(full, c, xn, uc, u_tank, k7);
   // squared scaled errors of this lane's states; summed in plant state order 0..N-1
   double e2[6];
 #pragma unroll
@@ -358,23 +316,16 @@ cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, Clo
   pdl_wait();
   pdl_trigger();   // single wave
   constexpr int kScen = 16, kItems = kScen * S::NCTRL * 3;
+  static_assert(kItems <= 96, "one linearisation item per lane of warps 1-3");
   __shared__ double y_sh[kScen][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.x * kScen;
   const bool early = lin_next && P.obs_states_free;
-  auto lin_items = [&](bool with_y) {
-    for (int idx = (warp - 1) * 32 + lane; idx < kItems; idx += 96) {
-      const int sl = idx / (3 * S::NCTRL), rem = idx % (3 * S::NCTRL);
-      const int b = b0 + sl;
-      if (b >= P.batch) continue;
-      double y[4] = {0.0, 0.0, 0.0, 0.0};   // not used by the state estimate when obs_states_free
-      if (with_y) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = y_sh[sl][i];
-      }
-      lin_part<S>(P, G, b, rem / 3, rem % 3, y, 0u);
-    }
-  };
+  // this lane's linearisation item (warps 1-3): scenario slot, sub-controller, part
+  const int idx = (warp - 1) * 32 + lane;
+  const int sl = idx / (3 * S::NCTRL), g = (idx % (3 * S::NCTRL)) / 3, part = idx % 3;
+  const bool item = warp != 0 && idx < kItems && b0 + sl < P.batch;
+  ObsPending<S> pend;
   if (warp == 0) {
     const int b = b0 + (lane >> 1), c = lane & 1;
     if (b < P.batch) {
@@ -385,22 +336,23 @@ cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, Clo
         for (int i = 0; i < 4; ++i) y_sh[lane >> 1][i] = y[i];
       }
     }
-  } else if (early) {
-    lin_items(false);
+  } else if (early && item) {
+    lin_part_early<S>(P, G, b0 + sl, g, part, pend);
   }
   if (!lin_next) return;
-  __syncthreads();
-  if (warp != 0 && !early) lin_items(true);
-  __syncthreads();   // every part has read the old observer state
-  if (warp == 0 && lane < kScen * S::NCTRL) {
-    const int sl = lane / S::NCTRL, b = b0 + sl;
-    if (b < P.batch) {
-      double y[4];
+  __syncthreads();   // the measurements are in y_sh; with `early`, every part has read the old observer state
+  double y[4] = {0.0, 0.0, 0.0, 0.0};
+  if (item) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = y_sh[sl][i];
-      lin_part<S>(P, G, b, lane % S::NCTRL, 3, y, 0u);
-    }
+    for (int i = 0; i < 4; ++i) y[i] = y_sh[sl][i];
   }
+  if (early) {
+    if (item && part == 0) lin_finish<S>(P, G, b0 + sl, g, pend, y);
+    return;
+  }
+  if (item) lin_part<S>(P, G, b0 + sl, g, part, y, 0u);
+  __syncthreads();   // every part has read the old observer state
+  if (item && part == 0) lin_part<S>(P, G, b0 + sl, g, 3, y, 0u);
 }
 
 // NerveCenter::Initialize + DistributedController::Initialize (nerve_center.h:98-104,186-203,

@@ -380,6 +380,78 @@ __device__ __forceinline__ void lin_part(const StepParams& P, const DeviceState&
   plant_linearize_part_x<S::PLANT>(part, xh, uf, wk + kWAc, kLD, wk + kWXc, kLD, inv, wk + kWCc);
 }
 
+// The same for the closed loop when StepParams::obs_states_free holds: the gain rows of the plant
+// states are zero, so x_hat+ = x_hat + dx[0..N) whatever the new measurement is, and the
+// linearisation can run while the plant is still being integrated.  lin_part_early fills part
+// `part` (0..2) of the hand-over record; the part-0 lane also returns what the observer update
+// still owes (ObsPending), and lin_finish completes and stores it once the measurement exists.
+// Every value is computed by the same expressions, in the same order, as in lin_part.
+template <class S>
+struct ObsPending {
+  double xh[S::N], dxs[S::N], dxn[4], yold[4], s[4];
+};
+
+template <class S>
+__device__ __forceinline__ void lin_part_early(const StepParams& P, const DeviceState& G, int scen, int g, int part,
+                                               ObsPending<S>& pend) {
+  constexpr int N = S::N, NOBS = S::NOBS, NIN = S::NIN;
+  const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
+  const double* ss = G.scen + size_t(scen) * kScenStateStride;
+  double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
+  double xh[N], dx[NOBS];
+#pragma unroll
+  for (int i = 0; i < N; ++i) xh[i] = gs[kOffXhat + i];
+#pragma unroll
+  for (int i = 0; i < NOBS; ++i) dx[i] = gs[kOffDx + i];
+  if (part == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      pend.s[r] = plant_c_row_dot<S::PLANT>(xh, r, dx) + dx[N + r];
+      pend.yold[r] = gs[kOffYold + r];
+      pend.dxn[r] = dx[N + r];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    xh[i] += dx[i];
+    if (part == 0) {
+      pend.xh[i] = xh[i];
+      pend.dxs[i] = dx[i];
+    }
+  }
+  double uf[NIN];
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) uf[i] = G.u_offset[size_t(scen) * NIN + i];
+  uf[0] += ss[0]; uf[3] += ss[1]; uf[4] += ss[2]; uf[7] += ss[3];
+  int inv[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) inv[P.c[g].ctrl_idx[c]] = c;
+  plant_linearize_part_x<S::PLANT>(part, xh, uf, wk + kWAc, kLD, wk + kWXc, kLD, inv, wk + kWCc);
+}
+
+template <class S>
+__device__ __forceinline__ void lin_finish(const StepParams& P, const DeviceState& G, int scen, int g,
+                                           const ObsPending<S>& pend, const double (&yv)[4]) {
+  constexpr int N = S::N;
+  double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
+  double ev[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ev[r] = yv[r] - pend.yold[r] - pend.s[r];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    gs[kOffXhat + i] = pend.xh[i];
+    gs[kOffDx + i] = pend.dxs[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double acc = pend.dxn[i];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc = fma(P.c[g].M[(N + i) * 4 + r], ev[r], acc);
+    gs[kOffDx + N + i] = acc;
+    gs[kOffYold + i] = yv[i];
+  }
+}
+
 template <class S>
 __global__ void __launch_bounds__(128)
 lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
