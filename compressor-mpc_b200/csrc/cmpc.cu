@@ -351,6 +351,10 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   P.n_iter = cfg->n_iterations;
   P.batch = cfg->batch;
   P.Ts = cfg->Ts;
+  {
+    const double Ts = cfg->Ts;
+    P.rk[0] = Ts; P.rk[1] = Ts * Ts / 2.0; P.rk[2] = Ts * Ts * Ts / 6.0; P.rk[3] = Ts * Ts * Ts * Ts / 24.0;
+  }
   const int B = cfg->batch, NC = h->NCTRL, N = h->N;
   for (int c = 0; c < NC; ++c) {
     CtrlParams& cp = P.c[c];

@@ -94,6 +94,7 @@ struct StepParams {
                          //    so the a-posteriori state estimate, and with it the linearisation point, does
                          //    not depend on the new measurement
   double Ts;
+  double rk[4];   // Ts, Ts^2/2, Ts^3/6, Ts^4/24: the RK4 polynomial of DiscretizeRK4, evaluated once on the host
   const double* yref;   // [NCTRL][p][NY]
   CtrlParams c[2];
 };
@@ -587,8 +588,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
     tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
     group_sync(g, TPC);
-    const double Ts = P.Ts;
-    const double k1 = Ts, k2 = Ts * Ts / 2.0, k3 = Ts * Ts * Ts / 6.0, k4 = Ts * Ts * Ts * Ts / 24.0;
+    const double k1 = P.rk[0], k2 = P.rk[1], k3 = P.rk[2], k4 = P.rk[3];
     for (int idx = t; idx < kNNP; idx += TPC) {   // pads included: they come out as exact zeros
       const int i = idx / kLD, j = idx % kLD;
       Acom[idx] = k1 * ((i == j && i < N) ? 1.0 : 0.0) + k2 * Ac[idx] + k3 * A2[idx] + k4 * A3[idx];
