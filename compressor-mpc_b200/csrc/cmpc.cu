@@ -187,7 +187,7 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
   // K1: discretisation, prediction, QP assembly; one CTA per scenario
   CU(launch_pdl(assemble_variant<S>(h->cfg.p), B, S::NCTRL * S::TPC, h->smem_bytes, st, h->P, h->G, y));
   if (ev) CU(cudaEventRecord(ev[2], st));
-  // K2: Jacobi sweeps + update; one warp per scenario
+  // K2: Jacobi sweeps + update; one lane pair per scenario
   CU(launch_pdl(solve_kernel<S>, (B * S::NCTRL + 63) / 64, 64, 0, st, h->P, h->G, u));
   h->P.ring_pos = (h->P.ring_pos + 1) % kRing;   // the oldest ring slot was consumed and refilled
   if (ev) CU(cudaEventRecord(ev[3], st));

@@ -193,9 +193,9 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 }
 
 // Operand fragments of one 8-row (A) or 8-column (B) block for K = 12 (three k-tiles).  The
-// operands live zero-padded in shared memory (every matrix slot is cleared at the start of the
-// step and only valid entries are ever written), so the loads need no predicates; rows or
-// columns beyond the matrix only feed output rows/columns that are never stored.
+// operands live zero-padded to K = 12 in shared memory (the pads are exact zeros: planted with the
+// seeds and reproduced by every product, see the load phase of assemble_kernel), so the loads need
+// no predicates; rows or columns beyond the 12 only feed output rows/columns that are never stored.
 __device__ __forceinline__ void frag_a(const double* A, int lda, int mt, int lane, double (&a)[3]) {
   const double* p = A + (8 * mt + (lane >> 2)) * lda + (lane & 3);
   a[0] = p[0];
