@@ -75,6 +75,7 @@ using ShapeNcoopPar = Shape<0, 2, 2, 2>;
 using ShapeCentSer = Shape<1, 4, 4, 1>;
 using ShapeCoopSer = Shape<1, 4, 2, 2>;
 using ShapeNcoopSer = Shape<1, 2, 2, 2>;
+using ShapeNcoopSerOld = Shape<1, 3, 2, 2>;
 
 #define CMPC_DISPATCH(shape_id, FN, ...)                            \
   switch (shape_id) {                                               \
@@ -84,6 +85,7 @@ using ShapeNcoopSer = Shape<1, 2, 2, 2>;
     case 3: return FN<ShapeCentSer>(__VA_ARGS__);                   \
     case 4: return FN<ShapeCoopSer>(__VA_ARGS__);                   \
     case 5: return FN<ShapeNcoopSer>(__VA_ARGS__);                  \
+    case 6: return FN<ShapeNcoopSerOld>(__VA_ARGS__);               \
     default: return fail(CMPC_ERR_UNSUPPORTED, "unsupported shape"); \
   }
 
@@ -91,8 +93,8 @@ int find_shape(const cmpc_config& c) {
   const int ny = c.n_controlled_outputs[0];
   if (c.n_controllers == 2 && c.n_controlled_outputs[1] != ny) return -1;
   struct Row { int plant, ny, nu, nctrl; };
-  const Row rows[6] = {{0, 3, 4, 1}, {0, 3, 2, 2}, {0, 2, 2, 2}, {1, 4, 4, 1}, {1, 4, 2, 2}, {1, 2, 2, 2}};
-  for (int i = 0; i < 6; ++i)
+  const Row rows[7] = {{0, 3, 4, 1}, {0, 3, 2, 2}, {0, 2, 2, 2}, {1, 4, 4, 1}, {1, 4, 2, 2}, {1, 2, 2, 2}, {1, 3, 2, 2}};
+  for (int i = 0; i < 7; ++i)
     if (rows[i].plant == c.plant && rows[i].ny == ny && rows[i].nu == c.n_sub_control_inputs &&
         rows[i].nctrl == c.n_controllers)
       return i;
@@ -264,7 +266,8 @@ int cmpc_plant_defaults(int plant, double* x, double* u) {
 
 int cmpc_default_config(int plant, int mode, int batch, cmpc_config* cfg) {
   if (!cfg) return fail(CMPC_ERR_ARG, "null cfg");
-  if ((plant != 0 && plant != 1) || mode < 0 || mode > 2) return fail(CMPC_ERR_ARG, "bad plant/mode");
+  if ((plant != 0 && plant != 1) || mode < 0 || mode > 3 || (mode == 3 && plant != 1))
+    return fail(CMPC_ERR_ARG, "bad plant/mode");
   std::memset(cfg, 0, sizeof *cfg);
   cfg->plant = plant;
   cfg->mode = mode;
@@ -296,6 +299,7 @@ int cmpc_default_config(int plant, int mode, int batch, cmpc_config* cfg) {
     if (plant == 0 && mode == 2) { set_out(0, {0, 3}); set_out(1, {1, 3}); }
     if (plant == 1 && mode == 1) { set_out(0, {0, 1, 2, 3}); set_out(1, {0, 1, 2, 3}); }
     if (plant == 1 && mode == 2) { set_out(0, {0, 1}); set_out(1, {2, 3}); }
+    if (plant == 1 && mode == 3) { set_out(0, {0, 1, 2}); set_out(1, {2, 3, 1}); }
   }
   return CMPC_OK;
 }

@@ -1,7 +1,7 @@
 // Driver in the shape of the reference's tests/*-with-timing.cc executables: reads a setup file,
 // runs the closed loop (controller + plant + actuator delay) for every simulation block on the
 // GPU and writes the reference's .dat records.
-//   cmpc_run_setup <setup-file> <parallel|serial> <centralized|cooperative|noncoop> [batch]
+//   cmpc_run_setup <setup-file> <parallel|serial> <centralized|cooperative|noncoop|noncoop-old> [batch]
 // Record layout and key order: SURVEY.md 3.1 (reconstructed tests/common-simulation.inc).
 #include <cstdio>
 #include <cstring>
@@ -26,13 +26,14 @@ static std::string FormatRow(const double* v, int n) {
 
 int main(int argc, char** argv) {
   if (argc < 4) {
-    std::fprintf(stderr, "usage: %s <setup-file> <parallel|serial> <centralized|cooperative|noncoop> [batch]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <setup-file> <parallel|serial> <centralized|cooperative|noncoop|noncoop-old> [batch]\n", argv[0]);
     return 2;
   }
   try {
     const int plant = std::strcmp(argv[2], "serial") == 0 ? CMPC_PLANT_SERIAL : CMPC_PLANT_PARALLEL;
     const int mode = std::strcmp(argv[3], "centralized") == 0 ? CMPC_MODE_CENTRALIZED
-                     : std::strcmp(argv[3], "cooperative") == 0 ? CMPC_MODE_COOPERATIVE : CMPC_MODE_NONCOOPERATIVE;
+                     : std::strcmp(argv[3], "cooperative") == 0 ? CMPC_MODE_COOPERATIVE
+                     : std::strcmp(argv[3], "noncoop-old") == 0 ? CMPC_MODE_NONCOOPERATIVE_OLD : CMPC_MODE_NONCOOPERATIVE;
     const int batch = argc > 4 ? std::atoi(argv[4]) : 1;
     SetupReader rd(argv[1]);
     double v[64];

@@ -19,7 +19,7 @@ from typing import List
 import numpy as np
 
 PLANT_PARALLEL, PLANT_SERIAL = 0, 1
-MODE_CENT, MODE_COOP, MODE_NCOOP = 0, 1, 2
+MODE_CENT, MODE_COOP, MODE_NCOOP, MODE_NCOOP_OLD = 0, 1, 2, 3
 
 # (plant, mode) -> (n_controllers, n_sub_control_inputs, controlled outputs per controller)
 # include/parallel_compressors_constants.h:70-93, include/serial_compressors_constants.h:84-109
@@ -30,6 +30,9 @@ SHAPES = {
     (PLANT_SERIAL, MODE_CENT): (1, 4, [[0, 1, 2, 3]]),
     (PLANT_SERIAL, MODE_COOP): (2, 2, [[0, 1, 2, 3], [0, 1, 2, 3]]),
     (PLANT_SERIAL, MODE_NCOOP): (2, 2, [[0, 1], [2, 3]]),
+    # SERIAL_CTRL_NONCOOP_OLD{1,2} (serial_compressors_constants.h:47-59,103-104): instantiated by the
+    # reference (distributed_controller_list.h:29-30) but used by none of its main programs
+    (PLANT_SERIAL, MODE_NCOOP_OLD): (2, 2, [[0, 1, 2], [2, 3, 1]]),
 }
 N_STATES = {PLANT_PARALLEL: 11, PLANT_SERIAL: 10}
 N_INPUTS = {PLANT_PARALLEL: 9, PLANT_SERIAL: 8}

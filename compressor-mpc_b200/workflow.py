@@ -36,7 +36,8 @@ else:
     from . import capi, controller, scenarios, setupfile
 
 PLANTS = {"parallel": setupfile.PLANT_PARALLEL, "serial": setupfile.PLANT_SERIAL}
-MODES = {"centralized": setupfile.MODE_CENT, "cooperative": setupfile.MODE_COOP, "noncoop": setupfile.MODE_NCOOP}
+MODES = {"centralized": setupfile.MODE_CENT, "cooperative": setupfile.MODE_COOP, "noncoop": setupfile.MODE_NCOOP,
+         "noncoop-old": setupfile.MODE_NCOOP_OLD}
 
 
 def _fmt_row(values) -> str:

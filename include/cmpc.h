@@ -27,7 +27,10 @@ extern "C" {
 
 enum { CMPC_OK = 0, CMPC_ERR_ARG = 1, CMPC_ERR_CUDA = 2, CMPC_ERR_UNSUPPORTED = 3, CMPC_ERR_STATE = 4 };
 enum { CMPC_PLANT_PARALLEL = 0, CMPC_PLANT_SERIAL = 1 };                 /* systems/{parallel,serial}_compressors.cc */
-enum { CMPC_MODE_CENTRALIZED = 0, CMPC_MODE_COOPERATIVE = 1, CMPC_MODE_NONCOOPERATIVE = 2 };
+enum { CMPC_MODE_CENTRALIZED = 0, CMPC_MODE_COOPERATIVE = 1, CMPC_MODE_NONCOOPERATIVE = 2,
+       /* serial plant only: the earlier non-cooperative output partition {0,1,2} / {2,3,1}
+        * (SERIAL_CTRL_NONCOOP_OLD{1,2}, serial_compressors_constants.h:47-59,103-104) */
+       CMPC_MODE_NONCOOPERATIVE_OLD = 3 };
 
 #define CMPC_N_CONTROL_INPUTS 4   /* plant inputs {0,3,4,7}: torque1, recycle1, torque2, recycle2 */
 #define CMPC_N_OUTPUTS 4

@@ -61,6 +61,8 @@ void DefaultConfig(int plant, int mode, SystemConfig* sc) {
   if (par && mode == 2) { ny = 2; int t0[4] = {0, 3, 0, 0}, t1[4] = {1, 3, 0, 0}; std::memcpy(o[0], t0, sizeof t0); std::memcpy(o[1], t1, sizeof t1); }
   if (!par && mode == 1) { ny = 4; int t[4] = {0, 1, 2, 3}; std::memcpy(o[0], t, sizeof t); std::memcpy(o[1], t, sizeof t); }
   if (!par && mode == 2) { ny = 2; int t0[4] = {0, 1, 0, 0}, t1[4] = {2, 3, 0, 0}; std::memcpy(o[0], t0, sizeof t0); std::memcpy(o[1], t1, sizeof t1); }
+  // SERIAL_CTRL_NONCOOP_OLD{1,2} (serial_compressors_constants.h:47-59,103-104)
+  if (!par && mode == 3) { ny = 3; int t0[4] = {0, 1, 2, 0}, t1[4] = {2, 3, 1, 0}; std::memcpy(o[0], t0, sizeof t0); std::memcpy(o[1], t1, sizeof t1); }
   for (int c = 0; c < 2; ++c) {
     sc->ctrl[c].n_controlled_outputs = ny;
     std::memcpy(sc->ctrl[c].controlled_output_indices, o[c], sizeof o[c]);

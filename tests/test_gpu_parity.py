@@ -264,6 +264,43 @@ def test_custom_observer_gain_matches_oracle(case, setups, pkg, gpu_lib):
     assert np.abs(d["traj"][:, :, 1 + n:5 + n] - g["traj"][:, :, 1 + n:5 + n]).max() > 1e-6
 
 
+def test_old_noncooperative_serial_partition_matches_oracle(setups, pkg, gpu_lib):
+    """SERIAL_CTRL_NONCOOP_OLD{1,2} (serial_compressors_constants.h:47-59,103-104): three controlled
+    outputs per sub-controller, {0,1,2} and {2,3,1}.  The reference instantiates it
+    (distributed_controller_list.h:29-30) but ships no setup file or recorded run for it, so parity
+    is against the oracle only."""
+    import copy
+    s = copy.deepcopy(setups["ncoop-ser"])
+    s.mode = pkg.setupfile.MODE_NCOOP_OLD
+    s.ywt = [np.diag([1900.0, 3.0, 100.0]), np.diag([1900.0, 3.0, 1.0])]
+    assert s.controlled_outputs == [[0, 1, 2], [2, 3, 1]]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 4, 150
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 40
+    g = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s).run_closed_loop(x0, be, bo, T, n_threads=4)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+    # step-level check of the prediction columns for the permuted output set {2,3,1}
+    nc = pkg.from_setup(s, batch=1)
+    nc.set_capture(True)
+    oc = ol.Oracle(s)
+    y0 = ol.plant_output(s.plant, x_def)
+    nc.Initialize(x_def, np.zeros(4), u_def, y0)
+    oc.initialize(x_def, np.zeros(4), u_def, y0)
+    y1 = y0 * (1 + 1e-3)
+    ug, uo = nc.GetNextInput(y1)[0], oc.get_next_input(y1)
+    assert np.allclose(ug, uo, rtol=1e-7, atol=1e-11)
+    for c in range(2):
+        Hg, fg, _ = nc.qp(c)
+        Ho, fo = oc.qp(c)
+        assert np.allclose(Hg[0], Ho, rtol=1e-9, atol=1e-9 * np.abs(Ho).max())
+        assert np.allclose(fg[0], fo, rtol=1e-8, atol=1e-9 * np.abs(fo).max())
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
