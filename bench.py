@@ -283,7 +283,10 @@ def main():
             traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": "assemble_kernel (discretise + predict + QP assembly)", "achieved": achieved_tf, "peak": peak_tf,
+    # "tensor": the kernel's dense algebra runs on the FP64 tensor cores (DMMA), which share the SM's
+    # FP64 pipe with DFMA; the denominator is that pipe's measured peak, not the bf16 figure
+    roofline = {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA)",
+                "kernel": "assemble_kernel (discretise + predict + QP assembly)", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                 "peak_source": "measured live by cmpc_measure_fp64_peak (DFMA %.1f, DMMA m8n8k4 %.1f TF); "
                                "MEASURED_PEAKS.json holds no FP64 figure" % (peak["dfma_tflops"], peak["dmma_m8n8k4_tflops"]),
