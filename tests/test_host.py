@@ -72,6 +72,14 @@ def test_c_abi_exports_every_declared_symbol(pkg):
     assert list(cfg.delays) == [0, 40, 0, 40] and list(cfg.control_input_indices[1]) == [2, 3, 0, 1]
     x, u = pkg.plant_defaults(1)
     assert np.array_equal(x, ol.plant_defaults(1)[0]) and np.array_equal(u, ol.plant_defaults(1)[1])
+    # every (plant, mode) the library knows gives the output partition of setupfile.SHAPES
+    for (plant, mode), (n_ctrl, n_sub, outs) in pkg.setupfile.SHAPES.items():
+        c = pkg.capi.default_config(plant, mode, 8)
+        assert (c.n_controllers, c.n_sub_control_inputs) == (n_ctrl, n_sub)
+        for k in range(n_ctrl):
+            assert list(c.controlled_output_indices[k])[: c.n_controlled_outputs[k]] == outs[k]
+    with pytest.raises(pkg.capi.CmpcError):
+        pkg.capi.default_config(0, pkg.setupfile.MODE_NCOOP_OLD, 8)   # the old partition is a serial-plant shape
 
 
 def test_product_fails_loudly_without_gpu(pkg):
