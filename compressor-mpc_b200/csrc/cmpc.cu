@@ -351,7 +351,8 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   P.p = cfg->p;
   P.b_max = (cfg->p + kBaby - 1) / kBaby;
   P.n_pow = ladder_stages(P.b_max);
-  P.ldr = giant_stride(P.b_max);
+  P.b_full = full_blocks(P.p, P.b_max);
+  P.ldr = giant_stride(giant_cols(P.b_max, P.b_full));
   P.n_iter = cfg->n_iterations;
   P.batch = cfg->batch;
   P.Ts = cfg->Ts;

@@ -58,6 +58,7 @@ constexpr int kWorkStride = 512, kWAc = 0, kWXc = 144, kWCc = 288, kWBF = 336;
 // kWBF holds what the a-priori observer update needs: base[N] (free response of the state part),
 // then the Bd columns of the undelayed inputs 0 and 2 (N each)
 constexpr int kRing = kDelay - 1;   // slots of one delay ring (the head is kept separately)
+constexpr int kMaxStageTilesLadder = 18;  // squaring (2) + up to 16 blocks x 6 columns / 8 per giant-step stage
 constexpr int kMaxPow = 8;           // stages of the power ladder: horizons up to 8 * 2^5 = 256
 constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
 
@@ -88,7 +89,7 @@ struct CtrlParams {
 };
 
 struct StepParams {
-  int p, b_max, n_pow, n_iter, batch, ldr;
+  int p, b_max, b_full, n_pow, n_iter, batch, ldr;   // b_full: full_blocks(p, b_max)
   int ring_pos;   // position of the oldest entry in the 39-slot delay rings (same for all scenarios)
   int obs_states_free;   // 1: no observer gain row of a plant state is non-zero (the reference's M = [0; I]),
                          //    so the a-posteriori state estimate, and with it the linearisation point, does
@@ -129,10 +130,23 @@ __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
 
-// Row stride of the giant-step matrix R (N x b_max*kNC): >= the column count and = 4 or 12
-// mod 16 so that the DMMA B-fragment loads (4 rows x 4 columns per half warp) hit 16 banks.
-__host__ __device__ constexpr int giant_stride(int b_max) {
-  int ld = b_max * kNC;
+// Columns of the giant-step matrix R.  Table rows k >= p - 40 are never read through a delayed
+// input column (those read 40 rows back) and rows k >= p - 39 never through the X40 column, so the
+// giant-step blocks b >= b_full keep only the three columns that are: cc = 0, 2 (undelayed inputs)
+// and 4 (f_d).  Block b < b_full: columns 6 b + cc; block b >= b_full: 6 b_full + 3 (b - b_full) + cc/2.
+__host__ __device__ constexpr int full_blocks(int p, int b_max) {
+  int f = (p - (kDelay - 1) + kBaby - 1) / kBaby;
+  if (f < 1) f = 1;   // block 0 also feeds the short convolution of the first 39 rows
+  return f > b_max ? b_max : f;
+}
+__host__ __device__ constexpr int giant_cols(int b_max, int b_full) { return kNC * b_full + 3 * (b_max - b_full); }
+__host__ __device__ constexpr int giant_col(int b, int cc, int b_full) {
+  return b < b_full ? kNC * b + cc : kNC * b_full + 3 * (b - b_full) + (cc >> 1);
+}
+// Row stride of R: >= the column count and = 4 or 12 mod 16 so that the DMMA B-fragment loads
+// (4 rows x 4 columns per half warp) hit 16 banks.
+__host__ __device__ constexpr int giant_stride(int cols) {
+  int ld = cols;
   while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
   return ld;
 }
@@ -171,12 +185,13 @@ struct SmemLayout {
     // E always starts where the (by then dead) powers are.  It can also overwrite its own inputs
     // L, R, V when every warp can hold its output tiles in registers; for longer horizons L, R, V
     // are placed behind it.
-    const int n_nt = (b_max * kNC + 7) / 8;
+    const int n_nt = (giant_cols(b_max, full_blocks(p, b_max)) + 7) / 8;
     e_alias = (n_nt + S::WPC - 1) / S::WPC <= kMaxStageTiles / S::NY;
     E = region;
     L = region + ((e_alias || n_scr > e_size) ? n_scr : e_size);
     R = L + kBaby * S::NY * kLD;
-    V = R + kLD * giant_stride(b_max);      // 12 rows: rows >= N stay zero (K padding)
+    const int r_cols = giant_cols(b_max, full_blocks(p, b_max));
+    V = R + kLD * giant_stride(r_cols);     // 12 rows: rows >= N stay zero (K padding)
     lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
     int end = lr_end > region + e_size ? lr_end : region + e_size;
     if (end < E + red_size) end = E + red_size;
@@ -507,7 +522,10 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   constexpr bool CT = PCT > 0;
   constexpr int kBmaxCt = (PCT + kBaby - 1) / kBaby;
   const int p = CT ? PCT : P.p, b_max = CT ? kBmaxCt : P.b_max;
-  const int ldr = CT ? giant_stride(kBmaxCt) : P.ldr, n_pow = CT ? ladder_stages(kBmaxCt) : P.n_pow;
+  constexpr int kBfullCt = full_blocks(PCT > 0 ? PCT : 1, kBmaxCt > 0 ? kBmaxCt : 1);
+  const int b_full = CT ? kBfullCt : P.b_full;
+  const int r_cols_all = giant_cols(b_max, b_full);   // columns of R
+  const int ldr = CT ? giant_stride(giant_cols(kBmaxCt, kBfullCt)) : P.ldr, n_pow = CT ? ladder_stages(kBmaxCt) : P.n_pow;
   const SmemLayout<S> lay(p, b_max, n_pow);
   const int ldE = lay.ldE;
   double* sm = smem + g * lay.total;
@@ -729,46 +747,60 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cq[0]);
       tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cq[1]);
     } else {
+      // giant steps: blocks [r_base, r_base + cnt) = Pm * blocks [0, cnt).  The first n_f targets are
+      // full blocks (their sources are the contiguous columns [0, 6 n_f)); the remaining n_p keep
+      // three columns each, gathered from columns cc = 0, 2, 4 of their source blocks.  All tiles of
+      // the stage (squaring, full, pruned) go through the tensor cores six at a time; with a
+      // compile-time horizon every count below is a constant and the code is straight-line.
       constexpr int r_base = 1 << (j - 3);
-      if (s < n_pow) {
-        // full doubling: column blocks [r_base, 2 r_base) = Pm * blocks [0, r_base); the first
-        // (up to) 4 column tiles are interleaved with the squaring
-        constexpr int r_cols = r_base * kNC, n_rt = (r_cols + 7) >> 3, n_first = n_rt < 4 ? n_rt : 4;
-        double bq[2 + n_first][3], cq[2 + n_first][2];
-        frag_b(Pm, kLD, 0, lane, bq[0]);
-        frag_b(Pm, kLD, 1, lane, bq[1]);
-#pragma unroll
-        for (int i = 0; i < n_first; ++i) frag_b(R, ldr, i, lane, bq[2 + i]);
-        mma3_shared_a_range<2 + n_first, 0, 2 + n_first>(cq, a, bq);
-#pragma unroll
-        for (int i = 0; i < n_first; ++i) tile_store(R, ldr, 0, r_base * kNC, kLD, r_cols, mt_w, i, lane, cq[2 + i]);
-        tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cq[0]);
-        tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cq[1]);
-#pragma unroll
-        for (int nt0 = 4; nt0 < n_rt; nt0 += 4) {
-          double bw[4][3], cw[4][2];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (nt0 + i < n_rt) frag_b(R, ldr, nt0 + i, lane, bw[i]);
-          mma3_shared_a<4>(cw, a, bw, n_rt - nt0 < 4 ? n_rt - nt0 : 4);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, kLD, r_cols, mt_w, nt0 + i, lane, cw[i]);
+      const bool do_sq = s < n_pow;   // the last stage needs no further power
+      const int cnt = do_sq ? r_base : b_max - r_base;
+      int n_f = b_full - r_base;
+      n_f = n_f < 0 ? 0 : (n_f > cnt ? cnt : n_f);
+      const int n_p = cnt - n_f;
+      const int f_cols = n_f * kNC, f_tiles = (f_cols + 7) >> 3;
+      const int p_cols = 3 * n_p, p_tiles = (p_cols + 7) >> 3;
+      const int p_col0 = giant_col(r_base + n_f, 0, b_full);   // first target column of the pruned part
+      const int sq_tiles = do_sq ? 2 : 0, n_tiles = sq_tiles + f_tiles + p_tiles;
+      auto load_tile = [&](int k, double (&bt)[3]) {
+        if (k < sq_tiles) {
+          frag_b(Pm, kLD, k, lane, bt);
+        } else if (k < sq_tiles + f_tiles) {
+          frag_b(R, ldr, k - sq_tiles, lane, bt);
+        } else {
+          const int m = 8 * (k - sq_tiles - f_tiles) + (lane >> 2);   // pruned-part column of this lane
+          const int col = m < p_cols ? giant_col(n_f + m / 3, 2 * (m % 3), b_full) : 0;
+          const double* pb = R + (lane & 3) * ldr + col;
+          bt[0] = pb[0];
+          bt[1] = pb[4 * ldr];
+          bt[2] = pb[8 * ldr];
         }
-      } else {
-        // last stage of the run: only the blocks up to b_max, and no further power
-        const int cnt = b_max - r_base;
-        const int r_cols = cnt > 0 ? cnt * kNC : 0;
-        const int n_rt = (r_cols + 7) >> 3;
-        for (int nt0 = 0; nt0 < n_rt; nt0 += 6) {
+      };
+      auto store_tile = [&](int k, const double (&ct)[2]) {
+        if (k < sq_tiles) {
+          tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, k, lane, ct);
+        } else if (k < sq_tiles + f_tiles) {
+          tile_store(R, ldr, 0, r_base * kNC, kLD, f_cols, mt_w, k - sq_tiles, lane, ct);
+        } else {
+          // the pruned part may start at an odd column: 8-byte stores
+          const int r = 8 * mt_w + (lane >> 2), m = 8 * (k - sq_tiles - f_tiles) + 2 * (lane & 3);
+          if (r < kLD) {
+            if (m < p_cols) R[r * ldr + p_col0 + m] = ct[0];
+            if (m + 1 < p_cols) R[r * ldr + p_col0 + m + 1] = ct[1];
+          }
+        }
+      };
+#pragma unroll
+      for (int k0 = 0; k0 < kMaxStageTilesLadder; k0 += 6) {
+        if (k0 < n_tiles) {
           double bw[6][3], cw[6][2];
 #pragma unroll
           for (int i = 0; i < 6; ++i)
-            if (nt0 + i < n_rt) frag_b(R, ldr, nt0 + i, lane, bw[i]);
-          mma3_shared_a<6>(cw, a, bw, n_rt - nt0 < 6 ? n_rt - nt0 : 6);
+            if (k0 + i < n_tiles) load_tile(k0 + i, bw[i]);
+          mma3_shared_a<6>(cw, a, bw, n_tiles - k0 < 6 ? n_tiles - k0 : 6);
 #pragma unroll
           for (int i = 0; i < 6; ++i)
-            if (nt0 + i < n_rt) tile_store(R, ldr, 0, r_base * kNC, kLD, r_cols, mt_w, nt0 + i, lane, cw[i]);
+            if (k0 + i < n_tiles) store_tile(k0 + i, cw[i]);
         }
       }
     }
@@ -788,7 +820,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // ---- phase 5: E[a + 8b][y][c] = (L_a R_b)[y][c]: (8 NY x N) (N x b_max kNC) on the tensor cores ----
   // warp w takes the column blocks nt = w, w + WPC, ...; the NY row blocks of L stay in registers.
   {
-    const int n_nt = (b_max * kNC + 7) >> 3;
+    const int n_nt = (r_cols_all + 7) >> 3;
     double al[NY][3];
 #pragma unroll
     for (int mt = 0; mt < NY; ++mt) frag_a(L, kLD, mt, lane, al[mt]);
@@ -796,11 +828,18 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     // channels (cc, cc + 1) of row a + 8 b (cc is even, so both stay inside block b)
     auto store_e = [&](int mt, int nt, const double (&c)[2]) {
       const int a = lane >> 2, n = 8 * nt + 2 * (lane & 3);
-      if (n < b_max * kNC) {
+      if (n < kNC * b_full) {
         const int b = n / kNC, cc = n % kNC;
         double* e = E + (mt * kNC + cc) * ldE + kBaby * b + a;
         e[0] = c[0];
         e[ldE] = c[1];
+      } else {
+        // blocks that keep cc = 0, 2, 4 only (6 b_full is even: a pair never straddles the two parts)
+#pragma unroll
+        for (int el = 0; el < 2; ++el) {
+          const int m = n + el - kNC * b_full;
+          if (n + el < r_cols_all) E[(mt * kNC + 2 * (m % 3)) * ldE + kBaby * (b_full + m / 3) + a] = c[el];
+        }
       }
     };
     if (warp == WPC - 1) {
@@ -853,8 +892,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   group_sync(g, TPC);
   if (G.etab) {
     double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NY * 5);
-    for (int idx = t; idx < p * NY * 5; idx += TPC)
-      ge[idx] = E[(((idx / 5) % NY) * kNC + idx % 5) * ldE + idx / (5 * NY)];
+    for (int idx = t; idx < p * NY * 5; idx += TPC) {
+      const int r = idx / (5 * NY), cc = idx % 5;
+      // delayed-input columns do not exist in the blocks b >= b_full (and nothing reads them there)
+      ge[idx] = ((cc & 1) && r >= kBaby * b_full) ? 0.0 : E[(((idx / 5) % NY) * kNC + cc) * ldE + r];
+    }
   }
 
   CMPC_TICK(3);
