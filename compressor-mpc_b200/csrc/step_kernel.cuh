@@ -714,10 +714,23 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     frag_a(Pm, kLD, mt_w, lane, a);
     if constexpr (j < 3) {
       constexpr int vc = 2 << j, l_cnt = 1 << j, n_lm = (l_cnt * NY + 7) >> 3;
-      double bq[3][3], cq[3][2];   // tiles 0,1: squaring; 2: V
+      // tiles 0,1: squaring; 2: V.  While V has at most 4 columns (j < 2) they ride in the unused half
+      // of the squaring's second column tile (Pm has columns 8..11 to offer there).
+      constexpr bool v_merged = j < 2;
+      constexpr int n_sq_tiles = v_merged ? 2 : 3;
+      double bq[3][3], cq[3][2];
       frag_b(Pm, kLD, 0, lane, bq[0]);
-      frag_b(Pm, kLD, 1, lane, bq[1]);
-      frag_b(V, kLDV, 0, lane, bq[2]);
+      if constexpr (v_merged) {
+        const int nl = lane >> 2;
+        const double* pb = (nl < 4) ? Pm + (lane & 3) * kLD + 8 + nl : V + (lane & 3) * kLDV + (nl - 4 < vc ? nl - 4 : 0);
+        const int ldb = (nl < 4) ? kLD : kLDV;
+        bq[1][0] = pb[0];
+        bq[1][1] = pb[4 * ldb];
+        bq[1][2] = pb[8 * ldb];
+      } else {
+        frag_b(Pm, kLD, 1, lane, bq[1]);
+        frag_b(V, kLDV, 0, lane, bq[2]);
+      }
       double al[2][3], bl[3], cl[2][2];
       frag_b(Pm, kLD, mt_w, lane, bl);      // column block nt = w of Pm
       // fragment row i of the doubling is (y, a) = (i >> j, i mod 2^j), i.e. row 8 y + a of L
@@ -731,9 +744,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         al[mt][1] = pl[4];
         al[mt][2] = pl[8];
       }
-      mma3_shared_a_range<3, 0, 3>(cq, a, bq);
+      mma3_shared_a_range<3, 0, n_sq_tiles>(cq, a, bq);
       mma3_shared_b_range<2, n_lm>(cl, al, bl);
-      tile_store(V, kLDV, 0, vc, kLD, vc, mt_w, 0, lane, cq[2]);
+      if constexpr (!v_merged) tile_store(V, kLDV, 0, vc, kLD, vc, mt_w, 0, lane, cq[2]);
 #pragma unroll
       for (int mt = 0; mt < n_lm; ++mt) {
         const int cc = 8 * mt_w + 2 * (lane & 3);
@@ -745,7 +758,18 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         }
       }
       tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cq[0]);
-      tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cq[1]);
+      if constexpr (v_merged) {
+        const int r = 8 * mt_w + (lane >> 2), q = lane & 3;
+        if (r < kLD) {
+          double2 v;
+          v.x = cq[1][0];
+          v.y = cq[1][1];
+          if (q < 2) *reinterpret_cast<double2*>(Pn + r * kLD + 8 + 2 * q) = v;                      // Pm^2 columns 8..11
+          else if (2 * (q - 2) < vc) *reinterpret_cast<double2*>(V + r * kLDV + vc + 2 * (q - 2)) = v;   // the new V columns
+        }
+      } else {
+        tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cq[1]);
+      }
     } else {
       // giant steps: blocks [r_base, r_base + cnt) = Pm * blocks [0, cnt).  The first n_f targets are
       // full blocks (their sources are the contiguous columns [0, 6 n_f)); the remaining n_p keep
