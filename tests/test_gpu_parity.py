@@ -301,6 +301,45 @@ def test_old_noncooperative_serial_partition_matches_oracle(setups, pkg, gpu_lib
         assert np.allclose(fg[0], fo, rtol=1e-8, atol=1e-9 * np.abs(fo).max())
 
 
+@pytest.mark.parametrize("case,seed", [("coop-par", 1), ("cent-ser", 2), ("ncoop-ser", 3), ("coop-ser", 4)])
+def test_random_weights_and_constraints_match_oracle(case, seed, setups, pkg, gpu_lib):
+    """The reference's setups only ever use diagonal weights.  Here: dense symmetric positive
+    definite output and input weights, shifted references, tighter and asymmetric input bounds."""
+    import copy
+    rng = np.random.default_rng(seed)
+    s = copy.deepcopy(setups[case])
+
+    def spd_like(m):
+        m = np.asarray(m, dtype=np.float64)
+        d = np.sqrt(np.diag(m))
+        n = len(d)
+        c = rng.uniform(-0.4, 0.4, (n, n))
+        c = (c + c.T) / 2
+        np.fill_diagonal(c, 1.0)
+        c = c @ c.T                      # positive definite correlation-like matrix
+        c /= np.sqrt(np.outer(np.diag(c), np.diag(c)))
+        return c * np.outer(d, d) * rng.uniform(0.5, 2.0)
+
+    s.ywt = [spd_like(w) for w in s.ywt]
+    s.uwt = spd_like(s.uwt)
+    s.yref = np.asarray(s.yref) * (1 + 2e-3 * rng.standard_normal(4))
+    s.lower = np.asarray(s.lower) * rng.uniform(0.3, 1.0, len(s.lower))
+    s.upper = np.asarray(s.upper) * rng.uniform(0.3, 1.0, len(s.upper))
+    s.rate_lower = np.asarray(s.rate_lower) * rng.uniform(0.05, 1.0, len(s.rate_lower))
+    s.rate_upper = np.asarray(s.rate_upper) * rng.uniform(0.05, 1.0, len(s.rate_upper))
+    x_def, _ = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 4, 140
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 30
+    g = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s).run_closed_loop(x0, be, bo, T, n_threads=4)
+    assert (g["status"] == 0).all() and (o["status"] == 0).all()
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
