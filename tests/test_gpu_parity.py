@@ -340,6 +340,30 @@ def test_random_weights_and_constraints_match_oracle(case, seed, setups, pkg, gp
     assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
 
 
+@pytest.mark.parametrize("case", ["coop-par", "cent-ser"])
+def test_infeasible_qp_gives_zero_move_like_the_reference(case, setups, pkg, gpu_lib):
+    """MpcQpSolver::SolveQP returns zeros when qpOASES fails (mpc_qp_solver.cc:66-69).  Contradictory
+    bounds on the first input make every QP infeasible: both sides must report a failed solve and
+    apply no move, step after step, and keep running."""
+    import copy
+    s = copy.deepcopy(setups[case])
+    s.lower = np.array(s.lower, dtype=np.float64); s.upper = np.array(s.upper, dtype=np.float64)
+    s.lower[0], s.upper[0] = 0.2, 0.1          # lower > upper
+    x_def, u_def = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 3, 25
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    g = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle(s).run_closed_loop(x0, be, bo, T, n_threads=3)
+    assert (g["status"] != 0).any()
+    assert np.array_equal(g["status"] != 0, o["status"] != 0)
+    ug, uo = g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n]
+    assert np.isfinite(g["traj"]).all()
+    assert rel_err(ug, uo, ATOL_U / RTOL_U) < RTOL_U
+    failed = (g["status"] != 0).all(axis=2)    # every sub-controller failed in that record
+    assert (np.abs(np.diff(ug, axis=1, prepend=0.0))[failed] == 0.0).all()
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
