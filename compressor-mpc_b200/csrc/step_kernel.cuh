@@ -650,7 +650,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // compile-time tile counts, so its DMMAs are straight-line code with nothing to predicate.
   auto stage = [&](auto Jc) {
     constexpr int j = decltype(Jc)::value, s = j + 1;
-    if (s > n_pow) return;
+    if (s > n_pow + (j == 3 ? 1 : 0)) return;   // (the delay-line block of stage 3 below runs even if stage 3 does not)
     const double* Pm = Pw + j * kNNP;
     double* Pn = Pw + s * kNNP;
     if constexpr (j == 3) {
@@ -707,6 +707,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       group_sync(g, TPC);
       CMPC_TICK(8);
     }
+    if (s > n_pow) return;   // horizons of at most 8 rows have no giant step: the ladder ends after the baby stages
     // this warp's row block of Pm multiplies: Pm (squaring), V (j < 3), R (j >= 3);
     // its column block of Pm is multiplied by the rows of L (j < 3).  All products of a stage
     // are independent: their DMMAs are issued interleaved.

@@ -364,6 +364,47 @@ def test_infeasible_qp_gives_zero_move_like_the_reference(case, setups, pkg, gpu
     assert (np.abs(np.diff(ug, axis=1, prepend=0.0))[failed] == 0.0).all()
 
 
+@pytest.mark.parametrize("B", [1, 17, 33])
+def test_ragged_batch_sizes(B, setups, pkg, gpu_lib):
+    """Batch sizes that do not fill a warp, a 16-scenario plant block or a 32-pair block: every
+    scenario of the ragged batch equals the same scenario run in a batch of its own size class."""
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    T = 60
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, 33, T)
+    be[:, 0] = 20
+    full = pkg.from_setup(s, batch=33).run_closed_loop(x0, be, bo, T)
+    part = pkg.from_setup(s, batch=B).run_closed_loop(x0[:B], be[:B], bo[:B], T)
+    for key in ("traj", "active", "objective", "status"):
+        assert np.array_equal(part[key], full[key][:B]), key
+
+
+def test_shortest_and_longest_horizons_and_rejected_configurations(setups, pkg, gpu_lib):
+    """p = 2 (one giant-step block, three ladder stages) and p = 256 (the longest the on-chip tables
+    take) against the oracle; configurations outside the built scope are refused, not approximated."""
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 2, 40
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 10
+    for p in (2, 9, 256):
+        g = pkg.from_setup(s, batch=B, p=p).run_closed_loop(x0, be, bo, T)
+        o = ol.Oracle(s, p=p).run_closed_loop(x0, be, bo, T, n_threads=2)
+        assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U, p
+        assert np.array_equal(g["active"], o["active"]), p
+    C = pkg.capi
+    for mutate in (lambda c: setattr(c, "p", 257), lambda c: setattr(c, "p", 1), lambda c: setattr(c, "batch", 0),
+                   lambda c: setattr(c, "m", 3), lambda c: c.delays.__setitem__(1, 20),
+                   lambda c: setattr(c, "n_controllers", 3), lambda c: c.n_controlled_outputs.__setitem__(1, 2)):
+        cfg = C.default_config(0, 1, 4)
+        mutate(cfg)
+        h = C.C.c_void_p()
+        rc = C.lib().cmpc_create(C.C.byref(cfg), 0, C.C.byref(h))
+        assert rc != 0 and not h.value, "configuration outside the scope must be refused"
+        assert C.lib().cmpc_last_error()
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
