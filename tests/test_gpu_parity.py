@@ -405,6 +405,34 @@ def test_shortest_and_longest_horizons_and_rejected_configurations(setups, pkg, 
         assert C.lib().cmpc_last_error()
 
 
+@pytest.mark.parametrize("case,p,n_iter", [("coop-par", 100, 1), ("coop-par", 100, 4), ("ncoop-par", 20, 9),
+                                            ("cent-ser", 5, 1), ("coop-ser", 39, 3), ("ncoop-ser", 40, 9),
+                                            ("cent-par", 8, 2)])
+def test_sweep_counts_short_horizons_and_reference_ramps(case, p, n_iter, setups, pkg, gpu_lib):
+    """Sweep counts other than the setups' 1 / 9, horizons around the 40-sample delay (no delayed row
+    at all, exactly one, ...) and below one giant step, with a reference that changes over the
+    horizon (SetOutputReference takes p rows, nerve_center.h:119-122)."""
+    s = setups[case]
+    x_def, _ = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 3, 90
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 30
+    ramp = np.asarray(s.yref)[None, :] * (1 + 1e-3 * np.linspace(0, 1, p)[:, None] * np.array([1.0, -1.0, 0.5, -0.5]))
+    nc = pkg.from_setup(s, batch=B, p=p, n_solver_iterations=n_iter)
+    nc.SetOutputReference(ramp)
+    o = ol.Oracle(s, p=p, n_iter=n_iter)
+    o.set_output_reference(ramp)
+    g = nc.run_closed_loop(x0, be, bo, T)
+    r = o.run_closed_loop(x0, be, bo, T, n_threads=3)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], r["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], r["active"])
+    assert rel_err(g["objective"], r["objective"], 1e-6) < RTOL_U
+    # the ramp matters: a constant reference gives another trajectory
+    c = pkg.from_setup(s, batch=B, p=p, n_solver_iterations=n_iter).run_closed_loop(x0, be, bo, T)
+    assert np.abs(c["traj"][:, :, 1 + n:5 + n] - g["traj"][:, :, 1 + n:5 + n]).max() > 1e-8
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
