@@ -138,7 +138,9 @@ int shape_setup(cmpc_handle* h) {
   if (h->smem_bytes > 227 * 1024)
     return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
   const AssembleFn fn = assemble_variant<S>(h->P.p);
-  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  // the limit belongs to the function, not to the handle: another handle with a longer horizon may
+  // share this instantiation, so it is opened up to what the SM offers
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   // ask for the largest shared-memory carveout: occupancy of this kernel is bounded by shared memory
   CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (getenv("CMPC_DEBUG")) {

@@ -433,6 +433,35 @@ def test_sweep_counts_short_horizons_and_reference_ramps(case, p, n_iter, setups
     assert np.abs(c["traj"][:, :, 1 + n:5 + n] - g["traj"][:, :, 1 + n:5 + n]).max() > 1e-8
 
 
+def test_handles_of_different_horizons_and_shapes_coexist(setups, pkg, gpu_lib):
+    """Several handles alive at once, created in an order that would break per-function launch
+    limits set per handle (two run-time horizons share one kernel instantiation), stepped in turn."""
+    cases = [("coop-par", 120), ("coop-par", 64), ("cent-ser", 100), ("coop-par", 250)]
+    B, T = 3, 30
+    ctl, ref = [], []
+    for case, p in cases:
+        s = setups[case]
+        x_def, _ = ol.plant_defaults(s.plant)
+        x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+        be[:, 0] = 10
+        ref.append(pkg.from_setup(s, batch=B, p=p).run_closed_loop(x0, be, bo, T)["traj"])
+        ctl.append((pkg.from_setup(s, batch=B, p=p), x0, be, bo, len(x_def)))
+    import torch
+    dev = torch.device("cuda", 0)
+    bufs = []
+    for nc, x0, be, bo, n in ctl:
+        bufs.append((torch.from_numpy(x0).to(dev), torch.from_numpy(be).to(dev), torch.from_numpy(bo).to(dev),
+                     torch.zeros((B, T, 1 + n + 8), dtype=torch.float64, device=dev)))
+    st = torch.cuda.current_stream().cuda_stream
+    for k in range(T):           # one record of every handle in turn
+        for (nc, x0, be, bo, n), (dx, dbe, dbo, dtraj) in zip(ctl, bufs):
+            nc.run_closed_loop_device(k, 1, T, dx.data_ptr(), be.shape[1], dbe.data_ptr(), dbo.data_ptr(),
+                                      dtraj.data_ptr(), 0, 0, 0, st)
+    torch.cuda.synchronize()
+    for r, (_, _, _, dtraj) in zip(ref, bufs):
+        assert np.array_equal(dtraj.cpu().numpy(), r)
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
