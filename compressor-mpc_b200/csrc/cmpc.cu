@@ -62,6 +62,7 @@ struct cmpc_handle {
   bool capture = false;
   bool timing = false;
   bool lin_ahead = false;   // closed loop: the next record's observer update + linearisation are already done
+  bool loop_started = false;   // the on-device plants (state, delay rings, measurement) belong to a running closed loop
   std::vector<cudaEvent_t> ev;   // pairs (start, stop) around control-step launches
   size_t ev_used = 0;
 };
@@ -211,6 +212,7 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
     int rc = launch_init<S>(h, A.x, h->d_uinit, h->d_uinitfull, A.y, st);
     if (rc) return rc;
     h->initialized = true;
+    h->loop_started = true;
   }
   double t = 0.0;
   for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;  // the reference driver accumulates t += Ts
@@ -517,6 +519,7 @@ int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
   if (rc) return rc;
   CU(cudaDeviceSynchronize());
   h->initialized = true;
+  h->loop_started = false;   // the controller was restarted on its own: the on-device plants no longer match it
   return CMPC_OK;
 }
 
@@ -575,7 +578,8 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
     return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
   const bool reinit = first_step == 0;
   if (reinit && !x0_dev) return fail(CMPC_ERR_ARG, "x0 required to start the scenarios");
-  if (!reinit && !h->initialized) return fail(CMPC_ERR_STATE, "scenarios were never started");
+  if (!reinit && !h->loop_started)
+    return fail(CMPC_ERR_STATE, "no closed loop to continue: start one with first_step = 0");
   ClosedLoopArrays A;
   A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
   A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;

@@ -120,7 +120,8 @@ int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_bl
 /* Device-resident variant: same arrays in device memory, runs on `stream`, no sync.
  * Runs records [first_step, first_step + n_steps) of a run whose arrays hold total_steps
  * records per scenario; first_step == 0 (re)starts the scenarios from x0_dev, later calls
- * continue from the state the handle holds. */
+ * continue from the state the handle holds (CMPC_ERR_STATE if there is no closed loop to
+ * continue: none was started, or cmpc_initialize has restarted the controller since). */
 int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int total_steps,
                                 const double* x0_dev, int n_blocks, const int32_t* block_end_dev,
                                 const double* block_off_dev, double* traj_dev,

@@ -492,6 +492,17 @@ def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     nc.Initialize(np.tile(x_def, (B, 1)), np.zeros(4), u_def, y0)
     u = nc.GetNextInput(y0)
     assert np.isfinite(u).all()
+    # ... and a controller restarted on its own has no closed loop to continue
+    with pytest.raises(pkg.capi.CmpcError, match="first_step = 0"):
+        nc.run_closed_loop_device(T // 2, 1, T, d_x0.data_ptr(), be.shape[1], d_be.data_ptr(), d_bo.data_ptr(),
+                                  d_traj.data_ptr(), 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+    fresh = pkg.from_setup(s, batch=B)
+    with pytest.raises(pkg.capi.CmpcError, match="first_step = 0"):
+        fresh.run_closed_loop_device(3, 1, T, d_x0.data_ptr(), be.shape[1], d_be.data_ptr(), d_bo.data_ptr(),
+                                     d_traj.data_ptr(), 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+    with pytest.raises(pkg.capi.CmpcError):
+        fresh.run_closed_loop_device(0, T + 1, T, d_x0.data_ptr(), be.shape[1], d_be.data_ptr(), d_bo.data_ptr(),
+                                     d_traj.data_ptr(), 0, 0, 0, torch.cuda.current_stream().cuda_stream)
 
 
 def test_no_launch_reads_uninitialised_shared_memory(pkg, gpu_lib):
