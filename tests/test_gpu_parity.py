@@ -462,6 +462,40 @@ def test_handles_of_different_horizons_and_shapes_coexist(setups, pkg, gpu_lib):
         assert np.array_equal(dtraj.cpu().numpy(), r)
 
 
+@pytest.mark.parametrize("case,p", [("coop-par", 200), ("coop-ser", 64), ("cent-par", 41), ("ncoop-par", 7)])
+def test_parity_hooks_at_other_horizons(case, p, setups, pkg, gpu_lib):
+    """GeneratePrediction / QP / linearisation hooks after a few host-facing steps at horizons
+    whose table layout differs from p = 100 (pruned columns start elsewhere, or nowhere)."""
+    s = setups[case]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    nc = pkg.from_setup(s, batch=2, p=p)
+    nc.set_capture(True)
+    o = ol.Oracle(s, p=p)
+    y0 = ol.plant_output(s.plant, x_def)
+    nc.Initialize(x_def, np.zeros(4), u_def, y0)
+    o.initialize(x_def, np.zeros(4), u_def, y0)
+    rng = np.random.default_rng(5)
+    for k in range(45):          # long enough for the delay lines to fill with non-zero moves
+        y = y0 * (1 + 2e-3 * rng.standard_normal(4))
+        ug, uo = nc.GetNextInput(y)[0], o.get_next_input(y)
+        assert np.allclose(ug, uo, rtol=1e-6, atol=1e-10), k
+    for c in range(nc.n_controllers):
+        Sug, Suog = nc.prediction(c)
+        Suo_, _, _, Suoo = o.prediction(c)
+        assert np.allclose(Sug[0], Suo_, rtol=1e-9, atol=1e-12)
+        if Suog is not None:
+            assert np.allclose(Suog[0], Suoo, rtol=1e-9, atol=1e-12)
+        Hg, fg, _ = nc.qp(c)
+        Ho, fo = o.qp(c)
+        assert np.allclose(Hg[0], Ho, rtol=1e-9, atol=1e-9 * np.abs(Ho).max())
+        assert np.allclose(fg[0], fo, rtol=1e-7, atol=1e-9 * np.abs(fo).max())
+        xg, dxg, _, uog = nc.controller_state(c)
+        xo, dxo, _, uoo = o.ctrl_state(c)
+        assert np.allclose(xg[0], xo, rtol=1e-10, atol=1e-13)
+        assert np.allclose(dxg[0], dxo, rtol=1e-8, atol=1e-12)
+        assert np.allclose(uog[0], uoo, rtol=1e-8, atol=1e-12)
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
