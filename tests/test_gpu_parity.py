@@ -588,19 +588,23 @@ def test_full_size_batch_properties(setups, golden, pkg, gpu_lib):
     assert np.unique(np.round(u[:, -1, 0], 9)).size > B // 2
 
 
-def test_setup_workflow_writes_reference_records(setups, golden, pkg, gpu_lib, tmp_path):
-    """setup file in, .dat records out: the reference's cooperative-serial workflow on the GPU."""
-    s = setups["coop-ser"]
-    f = tmp_path / "setup-coop-ser"
+@pytest.mark.parametrize("case", CASES)
+def test_setup_workflow_writes_reference_records(case, setups, golden, pkg, gpu_lib, tmp_path):
+    """setup file in, .dat records out: each of the reference's six workflows (run-all-tests.sh) on
+    the GPU, against the first 400 records of the reference's own output file."""
+    s = setups[case]
+    folder = "parallel" if s.plant == 0 else "serial"
+    n = 11 if s.plant == 0 else 10
+    f = tmp_path / f"setup-{case}"
     f.write_text(pkg.setupfile.format_setup(s))
-    r = pkg.workflow.run_setup(f, batch=2, out_dir=tmp_path / "serial", n_records=400)
-    assert [p.name for p in r["paths"]] == ["coop9.dat", "coop9.dat.s1"]
-    got = pkg.workflow.parse_records(r["paths"][0].read_text(), 10)
-    rec = golden["coop-ser/records"][:400]
-    assert got.shape == (400, 20)
+    r = pkg.workflow.run_setup(f, batch=2, out_dir=tmp_path / folder, n_records=400)
+    assert [p.name for p in r["paths"]] == [s.output_filename, s.output_filename + ".s1"]
+    got = pkg.workflow.parse_records(r["paths"][0].read_text(), n)
+    rec = golden[f"{case}/records"][:400]
+    assert got.shape == (400, 1 + n + 8 + 1)
     assert np.allclose(got[:, 0], rec[:, 0], rtol=1e-5)
-    assert (np.abs(got[:, 1:11] - rec[:, 1:11]) / np.maximum(np.abs(rec[:, 1:11]), 1e-3)).max() < 2e-5
-    assert np.abs(got[:, 11:15] - rec[:, 11:15]).max() < 1e-5
+    assert (np.abs(got[:, 1:1 + n] - rec[:, 1:1 + n]) / np.maximum(np.abs(rec[:, 1:1 + n]), 1e-3)).max() < 2e-5
+    assert np.abs(got[:, 1 + n:5 + n] - rec[:, 1 + n:5 + n]).max() < 1e-5
     assert (got[:, -1] > 0).all()
 
 
