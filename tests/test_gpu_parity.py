@@ -496,6 +496,44 @@ def test_parity_hooks_at_other_horizons(case, p, setups, pkg, gpu_lib):
         assert np.allclose(uog[0], uoo, rtol=1e-8, atol=1e-12)
 
 
+@pytest.mark.parametrize("case", ["coop-par", "ncoop-ser", "cent-par"])
+def test_per_controller_constraints_and_nonzero_initial_inputs(case, setups, pkg, gpu_lib):
+    """Different input constraints for the two sub-controllers and an Initialize with non-zero
+    u_init (the reference's drivers always start from zero): 60 host-facing steps, which also takes
+    the delay rings once around."""
+    s = setups[case]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    B = 2
+    nc = pkg.from_setup(s, batch=B)
+    o = ol.Oracle(s)
+    lo, up = np.asarray(s.lower, dtype=np.float64), np.asarray(s.upper, dtype=np.float64)
+    rlo, rup = np.asarray(s.rate_lower, dtype=np.float64), np.asarray(s.rate_upper, dtype=np.float64)
+    for c in range(nc.n_controllers):
+        k = 1.0 / (c + 2)
+        ic = pkg.InputConstraints(lo * k, up * k, rlo * k, rup * k)
+        nc.SetConstraints(c, ic)
+        ol.lib().orc_set_constraints(o.h, c, ol._p(ol.f64(lo * k)), ol._p(ol.f64(up * k)), ol._p(ol.f64(rlo * k)),
+                                     ol._p(ol.f64(rup * k)))
+    u_init = np.array([0.01, 0.02, -0.01, 0.03])
+    y0 = ol.plant_output(s.plant, x_def)
+    nc.Initialize(x_def, u_init, u_def, y0)
+    o.initialize(x_def, u_init, u_def, y0)
+    rng = np.random.default_rng(9)
+    act_seen = False
+    for k in range(60):
+        y = y0 * (1 + 4e-3 * rng.standard_normal(4))
+        ug, uo = nc.GetNextInput(y), o.get_next_input(y)
+        assert np.allclose(ug[0], uo, rtol=1e-6, atol=1e-10), k
+        assert np.array_equal(ug[0], ug[1])
+        info = nc.step_info()
+        for c in range(nc.n_controllers):
+            st, act, _ = o.last_qp_info(c)
+            assert info["status"][0, c] == st == 0
+            assert info["active"][0, c] == act
+            act_seen |= act != 0
+    assert act_seen or nc.n_controllers == 1, "the tightened constraints never became active"
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
