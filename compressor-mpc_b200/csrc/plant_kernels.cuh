@@ -12,6 +12,12 @@
 namespace cmpc {
 
 // One try_step of the controlled Dormand-Prince stepper (FSAL).  true: accepted.
+// odeint's integrate_adaptive puts no bound on the number of accepted steps: a plant state that runs
+// away (unphysical inputs) makes it take ever smaller steps for ever.  A kernel must not do that:
+// an interval stops after this many accepted steps (the nominal count is 1-4) and leaves the state
+// where it is; the records of such a scenario are no longer meaningful.
+constexpr int kMaxStepsPerInterval = 4000;
+
 template <int PLANT>
 __device__ bool dopri5_try_step(const double* u, double* x, double* dxdt, double* t, double* dt) {
   constexpr int N = PlantDims<PLANT>::N;
@@ -87,7 +93,7 @@ __device__ int integrate_interval(const double* u, double* x, double Ts) {
       if (++fails > 500) return -1;
     }
     fails = 0;
-    ++steps;
+    if (++steps >= kMaxStepsPerInterval) return -2;   // runaway plant state: see kMaxStepsPerInterval
   }
   return steps;
 }
@@ -182,7 +188,7 @@ __device__ int integrate_interval_pair(unsigned full, int c, const double uc[4],
       if (++fails > 500) return -1;
     }
     fails = 0;
-    ++steps;
+    if (++steps >= kMaxStepsPerInterval) return -2;   // runaway plant state: see kMaxStepsPerInterval
   }
   return steps;
 }

@@ -119,6 +119,12 @@ inline bool Dopri5TryStep(const Plant& plant, const double* u, int n, double* x,
   return true;
 }
 
+// odeint's integrate_adaptive puts no bound on the number of accepted steps: a plant state that runs
+// away (unphysical inputs) makes it take ever smaller steps for ever.  The GPU path must not do
+// that, so both sides stop an interval after this many accepted steps (the nominal count is 1-4)
+// and leave the state where it is; the records of such a scenario are no longer meaningful.
+constexpr int kMaxStepsPerInterval = 4000;
+
 // integrate_adaptive over one sampling interval [t0, t0+Ts] starting with dt = Ts.
 inline int IntegrateInterval(const Plant& plant, const double* u, double* x, double t0, double Ts,
                              int* n_rhs_evals) {
@@ -137,7 +143,7 @@ inline int IntegrateInterval(const Plant& plant, const double* u, double* x, dou
       if (++fails > 500) return -1;
     }
     fails = 0;
-    ++steps;
+    if (++steps >= kMaxStepsPerInterval) return -2;   // runaway plant state: see kMaxStepsPerInterval
   }
   return steps;
 }

@@ -534,6 +534,34 @@ def test_per_controller_constraints_and_nonzero_initial_inputs(case, setups, pkg
     assert act_seen or nc.n_controllers == 1, "the tightened constraints never became active"
 
 
+def test_runaway_plant_terminates(setups, pkg, gpu_lib):
+    """An unphysical input offset (three times the setup's disturbance) drives the serial plant into
+    a state where the adaptive integrator takes ever smaller steps (found by fuzzing: an unbounded
+    odeint loop, i.e. a kernel that never returns).  Both sides now stop an interval after 4000
+    accepted steps: the run must terminate, agree until the plant runs away, and report failed QPs
+    afterwards instead of hanging."""
+    import time
+    s = setups["cent-ser"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B, T = 2, 71
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 33
+    bo[:, 1, :] *= 3.0
+    t0 = time.time()
+    g = pkg.from_setup(s, batch=B, p=60, n_solver_iterations=8).run_closed_loop(x0, be, bo, T)
+    assert time.time() - t0 < 60
+    o = ol.Oracle(s, p=60, n_iter=8).run_closed_loop(x0, be, bo, T, n_threads=2)
+    fin = np.isfinite(o["traj"]).all(axis=2)
+    assert not fin.all(), "the scenario was meant to run away"
+    k_ok = int(np.argmin(fin.all(axis=0))) - 2     # records well before the first non-finite one
+    assert k_ok > 33
+    ug, uo = g["traj"][:, :k_ok, 1 + n:5 + n], o["traj"][:, :k_ok, 1 + n:5 + n]
+    assert rel_err(ug, uo, ATOL_U / RTOL_U) < 1e-5
+    assert np.isfinite(g["traj"][:, :k_ok]).all() and not np.isfinite(g["traj"]).all()
+    assert (g["status"][:, -1] != 0).all()      # the controller reports failed solves once the state is lost
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
