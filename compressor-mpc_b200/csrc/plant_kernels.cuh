@@ -87,15 +87,15 @@ __device__ int integrate_interval(const double* u, double* x, double Ts) {
   double t = 0.0, dt = Ts;
   int steps = 0, fails = 0;
   const double eps = 2.220446049250313e-16;
-  while (Ts - t > eps) {
+  while (Ts - t > eps && steps < kMaxStepsPerInterval) {
     if ((t + dt) - Ts > eps) dt = Ts - t;
     while (!dopri5_try_step<PLANT>(u, x, dxdt, &t, &dt)) {
       if (++fails > 500) return -1;
     }
     fails = 0;
-    if (++steps >= kMaxStepsPerInterval) return -2;   // runaway plant state: see kMaxStepsPerInterval
+    ++steps;
   }
-  return steps;
+  return steps;   // kMaxStepsPerInterval: the interval was cut short (runaway plant state)
 }
 
 // ---- lane-pair Dormand-Prince (same arithmetic per state as dopri5_try_step, same order of the
@@ -182,15 +182,15 @@ __device__ int integrate_interval_pair(unsigned full, int c, const double uc[4],
   double t = 0.0, dt = Ts;
   int steps = 0, fails = 0;
   const double eps = 2.220446049250313e-16;
-  while (Ts - t > eps) {
+  while (Ts - t > eps && steps < kMaxStepsPerInterval) {
     if ((t + dt) - Ts > eps) dt = Ts - t;
     while (!dopri5_try_step_pair<PLANT>(full, c, uc, u_tank, xs, k1, &t, &dt)) {
       if (++fails > 500) return -1;
     }
     fails = 0;
-    if (++steps >= kMaxStepsPerInterval) return -2;   // runaway plant state: see kMaxStepsPerInterval
+    ++steps;
   }
-  return steps;
+  return steps;   // kMaxStepsPerInterval: the interval was cut short (runaway plant state)
 }
 
 struct ClosedLoopArrays {

@@ -137,15 +137,15 @@ inline int IntegrateInterval(const Plant& plant, const double* u, double* x, dou
   int steps = 0, fails = 0;
   const double eps = std::numeric_limits<double>::epsilon();
   // less_with_sign(t, t_end, dt): (t_end - t) > eps
-  while (t_end - t > eps) {
+  while (t_end - t > eps && steps < kMaxStepsPerInterval) {
     if ((t + dt) - t_end > eps) dt = t_end - t;
     while (!Dopri5TryStep(plant, u, n, x, dxdt, &t, &dt, 1e-6, 1e-6, n_rhs_evals)) {
       if (++fails > 500) return -1;
     }
     fails = 0;
-    if (++steps >= kMaxStepsPerInterval) return -2;   // runaway plant state: see kMaxStepsPerInterval
+    ++steps;
   }
-  return steps;
+  return steps;   // kMaxStepsPerInterval: the interval was cut short (runaway plant state)
 }
 
 // SimulationSystem (simulation_system.h:17-117) reduced to what the driver uses.
