@@ -1,0 +1,76 @@
+"""Random sweep of GPU-vs-oracle closed loops: shapes, horizons, sweep counts, dense weights,
+scaled constraints, batch sizes and (sometimes) a three-fold disturbance.  Test infrastructure:
+`run(seed, n)` is used by tests/test_gpu_parity.py; as a script, `python tests/fuzz_parity.py SEED N`.
+
+Records are compared up to shortly before the oracle's first non-finite record: a three-fold
+disturbance can drive the serial plant into a runaway (both sides then cap the integrator and
+produce NaNs, whose pattern is not a parity statement)."""
+import copy
+import json
+import pathlib
+import sys
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import __graft_entry__ as ge  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+
+
+def run(seed: int, n_cfg: int, verbose: bool = False):
+    pkg = ge.load_package()
+    setups = {k: pkg.setupfile.setup_from_dict(v)
+              for k, v in json.load(open(ROOT / "tests" / "golden" / "setups.json")).items()}
+    cases = list(setups)
+    rng = np.random.default_rng(seed)
+
+    def spd_like(m):
+        m = np.asarray(m, dtype=np.float64)
+        d = np.sqrt(np.diag(m))
+        c = rng.uniform(-0.4, 0.4, (len(d), len(d)))
+        c = (c + c.T) / 2
+        np.fill_diagonal(c, 1.0)
+        c = c @ c.T
+        c /= np.sqrt(np.outer(np.diag(c), np.diag(c)))
+        return c * np.outer(d, d) * rng.uniform(0.5, 2.0)
+
+    bad = []
+    for it in range(n_cfg):
+        case = cases[rng.integers(len(cases))]
+        s = copy.deepcopy(setups[case])
+        p = int(rng.choice([rng.integers(2, 20), rng.integers(20, 60), rng.integers(60, 140), rng.integers(140, 257)]))
+        n_iter = int(rng.integers(1, 10))
+        if rng.random() < 0.5:
+            s.ywt = [spd_like(w) for w in s.ywt]
+            s.uwt = spd_like(s.uwt)
+        if rng.random() < 0.5:
+            for k in ("lower", "upper", "rate_lower", "rate_upper"):
+                setattr(s, k, np.asarray(getattr(s, k)) * rng.uniform(0.05, 1.0, len(getattr(s, k))))
+        x_def, _ = ol.plant_defaults(s.plant)
+        n = len(x_def)
+        B, T = int(rng.integers(1, 6)), int(rng.integers(20, 90))
+        x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T, first=int(rng.integers(0, 1000)))
+        be[:, 0] = rng.integers(5, T)
+        if rng.random() < 0.3:
+            bo[:, 1, :] *= 3.0
+        cfg = dict(case=case, p=p, n_iter=n_iter, B=B, T=T)
+        g = pkg.from_setup(s, batch=B, p=p, n_solver_iterations=n_iter).run_closed_loop(x0, be, bo, T)
+        o = ol.Oracle(s, p=p, n_iter=n_iter).run_closed_loop(x0, be, bo, T, n_threads=4)
+        fin = np.isfinite(o["traj"]).all(axis=2).all(axis=0)
+        K = T if fin.all() else max(int(np.argmin(fin)) - 3, 0)
+        ug, uo = g["traj"][:, :K, 1 + n:5 + n], o["traj"][:, :K, 1 + n:5 + n]
+        err = float(np.max(np.abs(ug - uo) / np.maximum(np.abs(uo), 1e-3))) if K else 0.0
+        ok = (err < 1e-6 and np.array_equal(g["active"][:, :K], o["active"][:, :K])
+              and np.array_equal(g["status"][:, :K] != 0, o["status"][:, :K] != 0))
+        if verbose:
+            print(it, cfg, "K", K, "err", err, "ok", ok, flush=True)
+        if not ok:
+            bad.append(dict(cfg, K=K, err=err))
+    return bad
+
+
+if __name__ == "__main__":
+    b = run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 40, verbose=True)
+    print(f"{len(b)} mismatches", b)

@@ -562,6 +562,14 @@ def test_runaway_plant_terminates(setups, pkg, gpu_lib):
     assert (g["status"][:, -1] != 0).all()      # the controller reports failed solves once the state is lost
 
 
+def test_random_configuration_sweep(pkg, gpu_lib):
+    """40 random configurations (tests/fuzz_parity.py): shapes x horizons 2..256 x sweep counts x
+    dense weights x scaled constraints x batch sizes x disturbances.  The sweep that found the
+    unbounded integrator loop; 360 configurations were clean when it was added."""
+    import fuzz_parity
+    assert fuzz_parity.run(seed=7, n_cfg=40) == []
+
+
 def test_closed_loop_in_pieces_and_handle_state(setups, pkg, gpu_lib):
     """The device-resident loop may be advanced in pieces (bench.py does, one record per call):
     the records are bit-identical to a single call.  A closed-loop run leaves the controller
