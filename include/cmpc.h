@@ -113,7 +113,11 @@ int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double
  * y0 = GetOutput(x0)); records [block_end[b][i-1], block_end[b][i]) run with plant-input
  * offsets block_off[b][i][:] added to the default input.
  * traj: B x n_steps x (1+n_states+4+4) = [t, x, u, y] per record (may be NULL);
- * qp_active / qp_objective / qp_status: B x n_steps x n_ctrl (may be NULL).  Host pointers. */
+ * qp_active / qp_objective / qp_status: B x n_steps x n_ctrl (may be NULL).  Host pointers.
+ * The plant integrator (Dormand-Prince with odeint's step control, simulation_system.h:66-133) ends
+ * a sampling interval after 4000 accepted steps: a scenario whose plant state runs away under an
+ * unphysical input then yields non-finite records and failed QPs instead of a call that never
+ * returns (the reference's loop is unbounded there). */
 int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
                          const int32_t* block_end, const double* block_off, double* traj,
                          uint32_t* qp_active, double* qp_objective, int32_t* qp_status);
