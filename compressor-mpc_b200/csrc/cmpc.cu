@@ -11,222 +11,39 @@
 #include <vector>
 
 #include "cmpc.h"
-#include "plant_kernels.cuh"
-#include "step_kernel.cuh"
+#include "handle.cuh"
 
 using namespace cmpc;
 
 namespace {
-
 thread_local std::string g_err;
+}
 
+namespace cmpc {
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
-
-#define CU(call)                                                                          \
-  do {                                                                                    \
-    cudaError_t e_ = (call);                                                              \
-    if (e_ != cudaSuccess)                                                                \
-      return fail(CMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
-  } while (0)
-
-template <typename T>
-cudaError_t dalloc(T** p, size_t n) {
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
-  if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
-  return e;
-}
-
-}  // namespace
-
-struct cmpc_handle {
-  cmpc_config cfg;
-  int device = 0;
-  int shape = -1;  // index into the instantiated shapes
-  int N = 0, NIN = 0, NV = 0, NVO = 0, NCTRL = 0;
-  StepParams P;
-  DeviceState G;
-  double* d_yref = nullptr;
-  double *d_y = nullptr, *d_u = nullptr;  // [B][4]
-  double *d_xinit = nullptr, *d_uinit = nullptr, *d_uinitfull = nullptr, *d_yinit = nullptr;
-  // closed loop
-  double *d_x = nullptr, *d_ring = nullptr;
-  int* d_block_end = nullptr;
-  double* d_block_off = nullptr;
-  size_t block_cap = 0;
-  size_t smem_bytes = 0;
-  int64_t launches = 0;
-  bool initialized = false;
-  bool capture = false;
-  bool timing = false;
-  bool lin_ahead = false;   // closed loop: the next record's observer update + linearisation are already done
-  bool loop_started = false;   // the on-device plants (state, delay rings, measurement) belong to a running closed loop
-  std::vector<cudaEvent_t> ev;   // pairs (start, stop) around control-step launches
-  size_t ev_used = 0;
-};
+extern const ShapeOps kOps_cent_par;
+extern const ShapeOps kOps_coop_par;
+extern const ShapeOps kOps_ncoop_par;
+extern const ShapeOps kOps_cent_ser;
+extern const ShapeOps kOps_coop_ser;
+extern const ShapeOps kOps_ncoop_ser;
+extern const ShapeOps kOps_ncoop_ser_old;
+const ShapeOps* const kShapeOps[kNumShapes] = {&kOps_cent_par, &kOps_coop_par, &kOps_ncoop_par, &kOps_cent_ser, &kOps_coop_ser, &kOps_ncoop_ser, &kOps_ncoop_ser_old};
+}  // namespace cmpc
 
 namespace {
-
-// ---- shape dispatch ---------------------------------------------------------------------
-using ShapeCentPar = Shape<0, 3, 4, 1>;
-using ShapeCoopPar = Shape<0, 3, 2, 2>;
-using ShapeNcoopPar = Shape<0, 2, 2, 2>;
-using ShapeCentSer = Shape<1, 4, 4, 1>;
-using ShapeCoopSer = Shape<1, 4, 2, 2>;
-using ShapeNcoopSer = Shape<1, 2, 2, 2>;
-using ShapeNcoopSerOld = Shape<1, 3, 2, 2>;
-
-#define CMPC_DISPATCH(shape_id, FN, ...)                            \
-  switch (shape_id) {                                               \
-    case 0: return FN<ShapeCentPar>(__VA_ARGS__);                   \
-    case 1: return FN<ShapeCoopPar>(__VA_ARGS__);                   \
-    case 2: return FN<ShapeNcoopPar>(__VA_ARGS__);                  \
-    case 3: return FN<ShapeCentSer>(__VA_ARGS__);                   \
-    case 4: return FN<ShapeCoopSer>(__VA_ARGS__);                   \
-    case 5: return FN<ShapeNcoopSer>(__VA_ARGS__);                  \
-    case 6: return FN<ShapeNcoopSerOld>(__VA_ARGS__);               \
-    default: return fail(CMPC_ERR_UNSUPPORTED, "unsupported shape"); \
-  }
 
 int find_shape(const cmpc_config& c) {
   const int ny = c.n_controlled_outputs[0];
   if (c.n_controllers == 2 && c.n_controlled_outputs[1] != ny) return -1;
-  struct Row { int plant, ny, nu, nctrl; };
-  const Row rows[7] = {{0, 3, 4, 1}, {0, 3, 2, 2}, {0, 2, 2, 2}, {1, 4, 4, 1}, {1, 4, 2, 2}, {1, 2, 2, 2}, {1, 3, 2, 2}};
-  for (int i = 0; i < 7; ++i)
-    if (rows[i].plant == c.plant && rows[i].ny == ny && rows[i].nu == c.n_sub_control_inputs &&
-        rows[i].nctrl == c.n_controllers)
-      return i;
+  for (int i = 0; i < kNumShapes; ++i) {
+    const ShapeOps& o = *kShapeOps[i];
+    if (o.plant == c.plant && o.ny == ny && o.nu == c.n_sub_control_inputs && o.nctrl == c.n_controllers) return i;
+  }
   return -1;
-}
-
-// Launch with programmatic stream serialisation (see pdl_wait / pdl_trigger in step_kernel.cuh).
-template <class... KArgs, class... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
-                       Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
-// The assemble_kernel instantiation for a prediction horizon: compile-time horizons for the
-// reference's p = 100 and the 2x sweep, run-time horizon otherwise.
-using AssembleFn = void (*)(StepParams, DeviceState, const double*);
-template <class S>
-AssembleFn assemble_variant(int p) {
-  if (p == 100) return assemble_kernel<S, 2, 100>;
-  if (p == 200) return assemble_kernel<S, 4, 200>;
-  return p <= 2 * S::TPC ? assemble_kernel<S, 2, 0> : assemble_kernel<S, 4, 0>;
-}
-
-template <class S>
-int shape_setup(cmpc_handle* h) {
-  const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow);
-  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 8);
-#ifdef CMPC_PHASE_TIMING
-  if (const char* e = getenv("CMPC_DEBUG_SMEM_MIN")) { size_t m = size_t(atol(e)); if (h->smem_bytes < m) h->smem_bytes = m; }  // occupancy experiments
-#endif
-  if (h->smem_bytes > 227 * 1024)
-    return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon too long for on-chip tables");
-  const AssembleFn fn = assemble_variant<S>(h->P.p);
-  // the limit belongs to the function, not to the handle: another handle with a longer horizon may
-  // share this instantiation, so it is opened up to what the SM offers
-  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  // ask for the largest shared-memory carveout: occupancy of this kernel is bounded by shared memory
-  CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  if (getenv("CMPC_DEBUG")) {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, S::NCTRL * S::TPC, h->smem_bytes);
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, fn);
-    fprintf(stderr, "[cmpc] assemble_kernel: smem %zu B/CTA, %d regs, %zu B local, occupancy %d CTAs/SM\n",
-            h->smem_bytes, fa.numRegs, fa.localSizeBytes, nb);
-  }
-  return CMPC_OK;
-}
-
-template <class S>
-int launch_init(cmpc_handle* h, const double* x, const double* u, const double* uf, const double* y,
-                cudaStream_t st) {
-  const int B = h->cfg.batch;
-  h->P.ring_pos = 0;
-  h->lin_ahead = false;
-  init_kernel<S><<<(B + 127) / 128, 128, 0, st>>>(B, h->G, x, u, uf, y, h->P);
-  h->launches++;
-  CU(cudaGetLastError());
-  return CMPC_OK;
-}
-
-template <class S>
-int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
-  const int B = h->cfg.batch;
-  cudaEvent_t* ev = nullptr;
-  if (h->timing) {
-    if (h->ev_used + 4 > h->ev.size()) {
-      const size_t old = h->ev.size();
-      h->ev.resize(old + 1024);
-      for (size_t i = old; i < h->ev.size(); ++i) CU(cudaEventCreate(&h->ev[i]));
-    }
-    ev = &h->ev[h->ev_used];
-    h->ev_used += 4;
-    CU(cudaEventRecord(ev[0], st));
-  }
-  // K0: observer + linearisation, 4 threads per (scenario, controller).  Inside a closed-loop run
-  // the previous record's plant kernel has already done this work (lin_ahead).
-  if (!h->lin_ahead) {
-    const int n_thr = B * S::NCTRL * 4;
-    CU(launch_pdl(lin_kernel<S>, (n_thr + 127) / 128, 128, 0, st, h->P, h->G, y));
-    h->launches++;
-  }
-  if (ev) CU(cudaEventRecord(ev[1], st));
-  // K1: discretisation, prediction, QP assembly; one CTA per scenario
-  CU(launch_pdl(assemble_variant<S>(h->cfg.p), B, S::NCTRL * S::TPC, h->smem_bytes, st, h->P, h->G, y));
-  if (ev) CU(cudaEventRecord(ev[2], st));
-  // K2: Jacobi sweeps + update; one lane pair per scenario
-  CU(launch_pdl(solve_kernel<S>, (B * S::NCTRL + 63) / 64, 64, 0, st, h->P, h->G, u));
-  h->P.ring_pos = (h->P.ring_pos + 1) % kRing;   // the oldest ring slot was consumed and refilled
-  if (ev) CU(cudaEventRecord(ev[3], st));
-  h->launches += 2;
-  CU(cudaGetLastError());
-  return CMPC_OK;
-}
-
-template <class S>
-int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double* x0,
-                       ClosedLoopArrays A, bool reinit, cudaStream_t st) {
-  const int B = h->cfg.batch;
-  if (reinit) {
-    cl_start_kernel<S::PLANT><<<(B + 63) / 64, 64, 0, st>>>(B, x0, A, h->d_uinit, h->d_uinitfull);
-    h->launches++;
-    CU(cudaGetLastError());
-    int rc = launch_init<S>(h, A.x, h->d_uinit, h->d_uinitfull, A.y, st);
-    if (rc) return rc;
-    h->initialized = true;
-    h->loop_started = true;
-  }
-  double t = 0.0;
-  for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;  // the reference driver accumulates t += Ts
-  for (int k = first_step; k < first_step + n_steps; ++k) {
-    int rc = launch_step<S>(h, A.y, A.u, st);
-    if (rc) return rc;
-    // plant side of record k, and the observer update + linearisation of record k + 1
-    CU(launch_pdl(cl_advance_kernel<S>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
-    h->lin_ahead = true;
-    h->launches++;
-    t += h->cfg.Ts;
-  }
-  CU(cudaGetLastError());
-  return CMPC_OK;
 }
 
 // StepParams::obs_states_free: do the observer gains leave the plant-state estimates alone?
@@ -238,11 +55,17 @@ void update_obs_states_free(cmpc_handle* h) {
   h->P.obs_states_free = free_ ? 1 : 0;
 }
 
-int check_handle(cmpc_handle* h) {
-  if (!h) return fail(CMPC_ERR_ARG, "null handle");
-  CU(cudaSetDevice(h->device));
-  return CMPC_OK;
-}
+// First statement of every entry point that takes a handle: argument check, then the handle's
+// device becomes current until the entry point returns (DeviceGuard puts the caller's back).
+#define CMPC_ENTER(h)                                                                              \
+  if (!(h)) return fail(CMPC_ERR_ARG, "null handle");                                              \
+  DeviceGuard device_guard_((h)->device);                                                          \
+  if (device_guard_.err != cudaSuccess)                                                            \
+    return fail(CMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(device_guard_.err))
+#define CMPC_ENTER_DEVICE(dev)                                                                     \
+  DeviceGuard device_guard_(dev);                                                                  \
+  if (device_guard_.err != cudaSuccess)                                                            \
+    return fail(CMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(device_guard_.err))
 
 }  // namespace
 
@@ -339,7 +162,7 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
     return fail(CMPC_ERR_CUDA, "no CUDA device: the control step has no CPU path");
   if (device < 0 || device >= n_dev) return fail(CMPC_ERR_ARG, "bad device index");
-  CU(cudaSetDevice(device));
+  CMPC_ENTER_DEVICE(device);
 
   cmpc_handle* h = new cmpc_handle;
   h->cfg = *cfg;
@@ -402,12 +225,13 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   A(dalloc(&h->d_yinit, size_t(B) * 4));
   A(dalloc(&h->d_x, size_t(B) * N));
   A(dalloc(&h->d_ring, size_t(B) * 2 * kDelay));
+  A(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   if (e != cudaSuccess) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   }
   P.yref = h->d_yref;
-  int rc = [&]() -> int { CMPC_DISPATCH(shape, shape_setup, h); }();
+  int rc = kShapeOps[shape]->setup(h);
   if (rc) {
     cmpc_destroy(h);
     return rc;
@@ -418,7 +242,8 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
 
 int cmpc_destroy(cmpc_handle* h) {
   if (!h) return CMPC_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard device_guard_(h->device);
+  cudaDeviceSynchronize();
   DeviceState& G = h->G;
   void* ptrs[] = {G.ctrl, G.guess, G.scen, G.u_offset, G.work, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
                   G.active, G.objective, G.ticks, h->d_yref, h->d_y, h->d_u, h->d_xinit, h->d_uinit,
@@ -426,12 +251,13 @@ int cmpc_destroy(cmpc_handle* h) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CMPC_OK;
 }
 
 int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* ywt) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   CtrlParams& cp = h->P.c[ctrl];
   const int ny = h->cfg.n_controlled_outputs[ctrl], nu = h->cfg.n_sub_control_inputs;
@@ -440,13 +266,24 @@ int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* 
       for (int j = 0; j < i; ++j)
         if (ywt[i * ny + j] != ywt[j * ny + i])
           return fail(CMPC_ERR_UNSUPPORTED, "ywt must be symmetric (H = Su' Q Su is kept as a symmetric matrix)");
+  // the reference adds the full u_weight_ to H (mpc_qp_solver.cc:27); the Hessian is kept as a
+  // symmetric matrix here, so an input weight that would make it non-symmetric is refused as well
+  if (uwt)
+    for (int i = 0; i < nu; ++i)
+      for (int j = 0; j < i; ++j)
+        if (uwt[i * nu + j] != uwt[j * nu + i])
+          return fail(CMPC_ERR_UNSUPPORTED, "uwt must be symmetric (H = Su' Q Su + R is kept as a symmetric matrix)");
+  for (int i = 0; uwt && i < nu * nu; ++i)
+    if (!std::isfinite(uwt[i])) return fail(CMPC_ERR_ARG, "uwt must be finite");
+  for (int i = 0; ywt && i < ny * ny; ++i)
+    if (!std::isfinite(ywt[i])) return fail(CMPC_ERR_ARG, "ywt must be finite");
   if (uwt) std::memcpy(cp.R, uwt, sizeof(double) * nu * nu);
   if (ywt) std::memcpy(cp.Q, ywt, sizeof(double) * ny * ny);
   return CMPC_OK;
 }
 
 int cmpc_set_output_reference(cmpc_handle* h, const double* yref) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!yref) return fail(CMPC_ERR_ARG, "null yref");
   // nerve_center.h:237-249: each controller keeps its controlled outputs of every prediction row
   const int p = h->cfg.p;
@@ -469,19 +306,28 @@ int cmpc_set_output_reference(cmpc_handle* h, const double* yref) {
 
 int cmpc_set_constraints(cmpc_handle* h, int ctrl, const double* lower, const double* upper,
                          const double* rate_lower, const double* rate_upper) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   if (!lower || !upper || !rate_lower || !rate_upper) return fail(CMPC_ERR_ARG, "null constraint array");
   CtrlParams& cp = h->P.c[ctrl];
+  // a bound is a finite number or +-infinity (kept as +-1e30, which no input ever reaches);
+  // NaN and an empty interval are refused here instead of surfacing as failed QPs at every step
+  auto clamp = [](double v) { return v > 1e30 ? 1e30 : (v < -1e30 ? -1e30 : v); };
   for (int i = 0; i < h->cfg.n_sub_control_inputs; ++i) {
-    cp.lower[i] = lower[i]; cp.upper[i] = upper[i];
-    cp.rate_lower[i] = rate_lower[i]; cp.rate_upper[i] = rate_upper[i];
+    if (std::isnan(lower[i]) || std::isnan(upper[i]) || std::isnan(rate_lower[i]) || std::isnan(rate_upper[i]))
+      return fail(CMPC_ERR_ARG, "constraint bounds must not be NaN");
+    if (lower[i] > upper[i] || rate_lower[i] > rate_upper[i])
+      return fail(CMPC_ERR_ARG, "constraint lower bound above upper bound");
+  }
+  for (int i = 0; i < h->cfg.n_sub_control_inputs; ++i) {
+    cp.lower[i] = clamp(lower[i]); cp.upper[i] = clamp(upper[i]);
+    cp.rate_lower[i] = clamp(rate_lower[i]); cp.rate_upper[i] = clamp(rate_upper[i]);
   }
   return CMPC_OK;
 }
 
 int cmpc_set_observer_gain(cmpc_handle* h, int ctrl, const double* M) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL || !M) return fail(CMPC_ERR_ARG, "bad argument");
   std::memcpy(h->P.c[ctrl].M, M, sizeof(double) * (h->N + kNDist) * 4);
   update_obs_states_free(h);
@@ -489,7 +335,7 @@ int cmpc_set_observer_gain(cmpc_handle* h, int ctrl, const double* M) {
 }
 
 int cmpc_set_capture(cmpc_handle* h, int on) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   const size_t B = h->cfg.batch, NC = h->NCTRL;
   const size_t ny = h->cfg.n_controlled_outputs[0];
   if (on && !h->G.lin) {
@@ -506,47 +352,46 @@ int cmpc_set_capture(cmpc_handle* h, int on) {
 
 int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
                     const double* u_init_full, const double* y_init) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!x_init || !u_init || !u_init_full || !y_init) return fail(CMPC_ERR_ARG, "null argument");
   const size_t B = h->cfg.batch;
+  CU(cudaDeviceSynchronize());   // nothing launched earlier (on any stream) may still be using the state
   CU(cudaMemcpy(h->d_xinit, x_init, B * h->N * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_uinit, u_init, B * 4 * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_uinitfull, u_init_full, B * h->NIN * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_yinit, y_init, B * 4 * sizeof(double), cudaMemcpyHostToDevice));
-  int rc = [&]() -> int {
-    CMPC_DISPATCH(h->shape, launch_init, h, h->d_xinit, h->d_uinit, h->d_uinitfull, h->d_yinit, nullptr);
-  }();
+  int rc = kShapeOps[h->shape]->init(h, h->d_xinit, h->d_uinit, h->d_uinitfull, h->d_yinit, h->stream);
   if (rc) return rc;
-  CU(cudaDeviceSynchronize());
+  CU(cudaStreamSynchronize(h->stream));
   h->initialized = true;
   h->loop_started = false;   // the controller was restarted on its own: the on-device plants no longer match it
   return CMPC_OK;
 }
 
 int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_dev, void* stream) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
   if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
   if (!y_dev || !u_dev) return fail(CMPC_ERR_ARG, "null argument");
-  CMPC_DISPATCH(h->shape, launch_step, h, y_dev, u_dev, static_cast<cudaStream_t>(stream));
+  return kShapeOps[h->shape]->step(h, y_dev, u_dev, static_cast<cudaStream_t>(stream));
 }
 
 int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
   if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
   if (!y || !u) return fail(CMPC_ERR_ARG, "null argument");
   const size_t bytes = size_t(h->cfg.batch) * 4 * sizeof(double);
-  CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, nullptr));
-  int rc = [&]() -> int { CMPC_DISPATCH(h->shape, launch_step, h, h->d_y, h->d_u, nullptr); }();
+  CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, h->stream));
+  int rc = kShapeOps[h->shape]->step(h, h->d_y, h->d_u, h->stream);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, nullptr));
-  CU(cudaStreamSynchronize(nullptr));
+  CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return CMPC_OK;
 }
 
 int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double* objective) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   const size_t n = size_t(h->cfg.batch) * h->NCTRL;
   CU(cudaDeviceSynchronize());
   if (status) CU(cudaMemcpy(status, h->G.status, n * sizeof(int), cudaMemcpyDeviceToHost));
@@ -556,7 +401,8 @@ int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double
 }
 
 int cmpc_debug_phase_ticks(cmpc_handle* h, long long* out /* B x 16 */) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
+  if (!out) return fail(CMPC_ERR_ARG, "null argument");
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(out, h->G.ticks, size_t(h->cfg.batch) * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return CMPC_OK;
@@ -572,7 +418,7 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
                                 const double* x0_dev, int n_blocks, const int32_t* block_end_dev,
                                 const double* block_off_dev, double* traj_dev, uint32_t* qp_active_dev,
                                 double* qp_objective_dev, int32_t* qp_status_dev, void* stream) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (first_step < 0 || n_steps < 0 || first_step + n_steps > total_steps || n_blocks < 1 ||
       !block_end_dev || !block_off_dev)
     return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
@@ -580,24 +426,44 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
   if (reinit && !x0_dev) return fail(CMPC_ERR_ARG, "x0 required to start the scenarios");
   if (!reinit && !h->loop_started)
     return fail(CMPC_ERR_STATE, "no closed loop to continue: start one with first_step = 0");
+  // The plant delay rings are indexed by the record number and the trajectory slots by
+  // (record, total_steps): a continuation that does not pick up exactly where the previous call
+  // stopped, with the same run description, would silently desynchronise them.
+  if (!reinit && (first_step != h->loop_next || total_steps != h->loop_total || n_blocks != h->loop_blocks ||
+                  block_end_dev != h->loop_block_end || block_off_dev != h->loop_block_off ||
+                  traj_dev != h->loop_traj))
+    return fail(CMPC_ERR_STATE, "continuation does not match the running closed loop (expected first_step = " +
+                                    std::to_string(h->loop_next) + " of " + std::to_string(h->loop_total) +
+                                    " records and the same block / trajectory arrays)");
   ClosedLoopArrays A;
   A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
   A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;
   A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
   A.qp_status = qp_status_dev; A.n_steps = total_steps;
-  CMPC_DISPATCH(h->shape, launch_closed_loop, h, first_step, n_steps, x0_dev, A, reinit,
-                static_cast<cudaStream_t>(stream));
+  const int rc = kShapeOps[h->shape]->closed_loop(h, first_step, n_steps, x0_dev, A, reinit,
+                                                   static_cast<cudaStream_t>(stream));
+  if (rc == CMPC_OK) {
+    h->loop_next = first_step + n_steps;
+    h->loop_total = total_steps;
+    h->loop_blocks = n_blocks;
+    h->loop_block_end = block_end_dev;
+    h->loop_block_off = block_off_dev;
+    h->loop_traj = traj_dev;
+  } else {
+    h->loop_started = false;   // part of the launches may have gone out: the run cannot be continued
+  }
+  return rc;
 }
 
 int cmpc_set_timing(cmpc_handle* h, int on) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   h->timing = on != 0;
   h->ev_used = 0;
   return CMPC_OK;
 }
 
 int cmpc_get_timing(cmpc_handle* h, int64_t* n_steps, double* step_ms, double* assemble_ms) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   CU(cudaDeviceSynchronize());
   double total = 0.0, asm_ms = 0.0;
   for (size_t i = 0; i + 3 < h->ev_used; i += 4) {
@@ -617,44 +483,55 @@ int cmpc_get_timing(cmpc_handle* h, int64_t* n_steps, double* step_ms, double* a
 int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
                          const int32_t* block_end, const double* block_off, double* traj,
                          uint32_t* qp_active, double* qp_objective, int32_t* qp_status) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!x0 || !block_end || !block_off || n_blocks < 1 || n_steps < 0)
     return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
   const size_t B = h->cfg.batch, NC = h->NCTRL, REC = 1 + h->N + 8;
-  double *d_traj = nullptr, *d_obj = nullptr;
-  unsigned* d_act = nullptr;
-  int* d_st = nullptr;
+  for (size_t b = 0; b < B; ++b)
+    for (int i = 0; i < n_blocks; ++i) {
+      const int32_t e = block_end[b * n_blocks + i];
+      if (e < 0 || (i > 0 && e < block_end[b * n_blocks + i - 1]))
+        return fail(CMPC_ERR_ARG, "block_end must be non-negative and non-decreasing per scenario");
+    }
+  CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(h->d_xinit, x0, B * h->N * sizeof(double), cudaMemcpyHostToDevice));
   if (h->block_cap < B * n_blocks) {
     if (h->d_block_end) cudaFree(h->d_block_end);
     if (h->d_block_off) cudaFree(h->d_block_off);
+    h->d_block_end = nullptr;
+    h->d_block_off = nullptr;
+    h->block_cap = 0;
     CU(dalloc(&h->d_block_end, B * n_blocks));
     CU(dalloc(&h->d_block_off, B * n_blocks * h->NIN));
     h->block_cap = B * n_blocks;
   }
   CU(cudaMemcpy(h->d_block_end, block_end, B * n_blocks * sizeof(int), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_block_off, block_off, B * n_blocks * h->NIN * sizeof(double), cudaMemcpyHostToDevice));
-  if (traj) CU(dalloc(&d_traj, B * n_steps * REC));
-  if (qp_active) CU(dalloc(&d_act, B * n_steps * NC));
-  if (qp_objective) CU(dalloc(&d_obj, B * n_steps * NC));
-  if (qp_status) CU(dalloc(&d_st, B * n_steps * NC));
-  int rc = cmpc_run_closed_loop_device(h, 0, n_steps, n_steps, h->d_xinit, n_blocks, h->d_block_end,
-                                       h->d_block_off, d_traj, d_act, d_obj, d_st, nullptr);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (rc == CMPC_OK && e != cudaSuccess) rc = fail(CMPC_ERR_CUDA, cudaGetErrorString(e));
-  if (rc == CMPC_OK) {
-    if (traj) cudaMemcpy(traj, d_traj, B * n_steps * REC * sizeof(double), cudaMemcpyDeviceToHost);
-    if (qp_active) cudaMemcpy(qp_active, d_act, B * n_steps * NC * sizeof(unsigned), cudaMemcpyDeviceToHost);
-    if (qp_objective) cudaMemcpy(qp_objective, d_obj, B * n_steps * NC * sizeof(double), cudaMemcpyDeviceToHost);
-    if (qp_status) cudaMemcpy(qp_status, d_st, B * n_steps * NC * sizeof(int), cudaMemcpyDeviceToHost);
-  }
-  cudaFree(d_traj); cudaFree(d_act); cudaFree(d_obj); cudaFree(d_st);
-  return rc;
+  DevBuf<double> d_traj, d_obj;
+  DevBuf<unsigned> d_act;
+  DevBuf<int> d_st;
+  const size_t nrec = B * size_t(n_steps);
+  if (traj) CU(d_traj.alloc(nrec * REC));
+  if (qp_active) CU(d_act.alloc(nrec * NC));
+  if (qp_objective) CU(d_obj.alloc(nrec * NC));
+  if (qp_status) CU(d_st.alloc(nrec * NC));
+  if (int rc = cmpc_run_closed_loop_device(h, 0, n_steps, n_steps, h->d_xinit, n_blocks, h->d_block_end,
+                                           h->d_block_off, d_traj.p, d_act.p, d_obj.p, d_st.p, h->stream))
+    return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  if (traj) CU(d_traj.download(traj, nrec * REC));
+  if (qp_active) CU(d_act.download(qp_active, nrec * NC));
+  if (qp_objective) CU(d_obj.download(qp_objective, nrec * NC));
+  if (qp_status) CU(d_st.download(qp_status, nrec * NC));
+  // the temporaries go away with this call: the run cannot be continued through the device variant
+  h->loop_traj = nullptr;
+  h->loop_started = false;
+  return CMPC_OK;
 }
 
 // ---- parity hooks ---------------------------------------------------------------------
 int cmpc_get_linearization(cmpc_handle* h, int ctrl, double* Aorig, double* Bd, double* f) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!h->G.lin) return fail(CMPC_ERR_STATE, "enable cmpc_set_capture before the step");
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   const int N = h->N, rec = N * N + N * 5;
@@ -674,7 +551,7 @@ int cmpc_get_linearization(cmpc_handle* h, int ctrl, double* Aorig, double* Bd, 
 }
 
 int cmpc_get_qp(cmpc_handle* h, int ctrl, double* H, double* f, double* Gx) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   const size_t B = h->cfg.batch, NC = h->NCTRL, NV = h->NV, NVO = h->NVO;
   CU(cudaDeviceSynchronize());
@@ -689,7 +566,7 @@ int cmpc_get_qp(cmpc_handle* h, int ctrl, double* H, double* f, double* Gx) {
 }
 
 int cmpc_generate_prediction(cmpc_handle* h, int ctrl, double* Su, double* Su_other) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (!h->G.etab) return fail(CMPC_ERR_STATE, "enable cmpc_set_capture before the step");
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   // Rebuild Su / Su_other from the impulse-response table exactly as GeneratePrediction
@@ -725,7 +602,7 @@ int cmpc_generate_prediction(cmpc_handle* h, int ctrl, double* Su, double* Su_ot
 
 int cmpc_get_controller_state(cmpc_handle* h, int ctrl, double* x_hat, double* dx_aug, double* y_old,
                               double* u_old) {
-  if (int rc = check_handle(h)) return rc;
+  CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   const size_t B = h->cfg.batch;
   std::vector<double> buf(B * h->NCTRL * kCtrlStateStride);
@@ -755,81 +632,66 @@ int cmpc_solve_qp(int device, int nq, int nv, const double* H, const double* f, 
   if (nq <= 0 || (nv != 4 && nv != 8)) return fail(CMPC_ERR_ARG, "nv must be 4 or 8");
   if (!H || !f || !lb || !ub || !lbA || !ubA || !guess_io || !z || !active || !objective || !status)
     return fail(CMPC_ERR_ARG, "null argument");
-  CU(cudaSetDevice(device));
-  double *dH, *df, *dlb, *dub, *dlbA, *dubA, *dz, *dobj;
-  unsigned *dg, *dact;
-  int* dst;
+  CMPC_ENTER_DEVICE(device);
+  DevBuf<double> dH, df, dlb, dub, dlbA, dubA, dz, dobj;
+  DevBuf<unsigned> dg, dact;
+  DevBuf<int> dst;
   const size_t n = nq;
-  CU(dalloc(&dH, n * nv * nv)); CU(dalloc(&df, n * nv)); CU(dalloc(&dlb, n * nv)); CU(dalloc(&dub, n * nv));
-  CU(dalloc(&dlbA, n * nv)); CU(dalloc(&dubA, n * nv)); CU(dalloc(&dz, n * nv)); CU(dalloc(&dobj, n));
-  CU(dalloc(&dg, n)); CU(dalloc(&dact, n)); CU(dalloc(&dst, n));
-  CU(cudaMemcpy(dH, H, n * nv * nv * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(df, f, n * nv * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dlb, lb, n * nv * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dub, ub, n * nv * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dlbA, lbA, n * nv * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dubA, ubA, n * nv * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dg, guess_io, n * sizeof(unsigned), cudaMemcpyHostToDevice));
+  CU(dH.upload(H, n * nv * nv)); CU(df.upload(f, n * nv)); CU(dlb.upload(lb, n * nv)); CU(dub.upload(ub, n * nv));
+  CU(dlbA.upload(lbA, n * nv)); CU(dubA.upload(ubA, n * nv)); CU(dg.upload(guess_io, n));
+  CU(dz.alloc(n * nv)); CU(dobj.alloc(n)); CU(dact.alloc(n)); CU(dst.alloc(n));
   if (nv == 4)
-    qp_kernel<4><<<(nq + 63) / 64, 64>>>(nq, dH, df, dlb, dub, dlbA, dubA, dg, dz, dact, dobj, dst);
+    qp_kernel<4><<<(nq + 63) / 64, 64>>>(nq, dH.p, df.p, dlb.p, dub.p, dlbA.p, dubA.p, dg.p, dz.p, dact.p, dobj.p, dst.p);
   else
-    qp_kernel<8><<<(nq + 63) / 64, 64>>>(nq, dH, df, dlb, dub, dlbA, dubA, dg, dz, dact, dobj, dst);
+    qp_kernel<8><<<(nq + 63) / 64, 64>>>(nq, dH.p, df.p, dlb.p, dub.p, dlbA.p, dubA.p, dg.p, dz.p, dact.p, dobj.p, dst.p);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(z, dz, n * nv * sizeof(double), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(guess_io, dg, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(active, dact, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(objective, dobj, n * sizeof(double), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(status, dst, n * sizeof(int), cudaMemcpyDeviceToHost));
-  cudaFree(dH); cudaFree(df); cudaFree(dlb); cudaFree(dub); cudaFree(dlbA); cudaFree(dubA);
-  cudaFree(dz); cudaFree(dobj); cudaFree(dg); cudaFree(dact); cudaFree(dst);
+  CU(dz.download(z, n * nv));
+  CU(dg.download(guess_io, n));
+  CU(dact.download(active, n));
+  CU(dobj.download(objective, n));
+  CU(dst.download(status, n));
   return CMPC_OK;
 }
 
 int cmpc_plant_eval(int device, int plant, int nq, const double* x, const double* u, double* dxdt,
                     double* y, double* A, double* Bc, double* C) {
   if ((plant != 0 && plant != 1) || nq <= 0 || !x || !u) return fail(CMPC_ERR_ARG, "bad argument");
-  CU(cudaSetDevice(device));
+  CMPC_ENTER_DEVICE(device);
   const size_t n = nq, N = plant == 0 ? 11 : 10, NIN = plant == 0 ? 9 : 8;
-  double *dx, *du, *dd, *dy, *dA, *dB, *dC;
-  CU(dalloc(&dx, n * N)); CU(dalloc(&du, n * NIN)); CU(dalloc(&dd, n * N)); CU(dalloc(&dy, n * 4));
-  CU(dalloc(&dA, n * N * N)); CU(dalloc(&dB, n * N * 4)); CU(dalloc(&dC, n * 4 * N));
-  CU(cudaMemcpy(dx, x, n * N * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(du, u, n * NIN * sizeof(double), cudaMemcpyHostToDevice));
+  DevBuf<double> dx, du, dd, dy, dA, dB, dC;
+  CU(dx.upload(x, n * N)); CU(du.upload(u, n * NIN));
+  CU(dd.alloc(n * N)); CU(dy.alloc(n * 4)); CU(dA.alloc(n * N * N)); CU(dB.alloc(n * N * 4)); CU(dC.alloc(n * 4 * N));
   if (plant == 0)
-    plant_eval_kernel<0><<<(nq + 63) / 64, 64>>>(nq, dx, du, dd, dy, dA, dB, dC);
+    plant_eval_kernel<0><<<(nq + 63) / 64, 64>>>(nq, dx.p, du.p, dd.p, dy.p, dA.p, dB.p, dC.p);
   else
-    plant_eval_kernel<1><<<(nq + 63) / 64, 64>>>(nq, dx, du, dd, dy, dA, dB, dC);
+    plant_eval_kernel<1><<<(nq + 63) / 64, 64>>>(nq, dx.p, du.p, dd.p, dy.p, dA.p, dB.p, dC.p);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
-  if (dxdt) CU(cudaMemcpy(dxdt, dd, n * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (y) CU(cudaMemcpy(y, dy, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
-  if (A) CU(cudaMemcpy(A, dA, n * N * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (Bc) CU(cudaMemcpy(Bc, dB, n * N * 4 * sizeof(double), cudaMemcpyDeviceToHost));
-  if (C) CU(cudaMemcpy(C, dC, n * 4 * N * sizeof(double), cudaMemcpyDeviceToHost));
-  cudaFree(dx); cudaFree(du); cudaFree(dd); cudaFree(dy); cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  if (dxdt) CU(dd.download(dxdt, n * N));
+  if (y) CU(dy.download(y, n * 4));
+  if (A) CU(dA.download(A, n * N * N));
+  if (Bc) CU(dB.download(Bc, n * N * 4));
+  if (C) CU(dC.download(C, n * 4 * N));
   return CMPC_OK;
 }
 
 int cmpc_plant_integrate(int device, int plant, int nq, double* x, const double* u, double Ts,
                          int32_t* n_substeps) {
   if ((plant != 0 && plant != 1) || nq <= 0 || !x || !u) return fail(CMPC_ERR_ARG, "bad argument");
-  CU(cudaSetDevice(device));
+  CMPC_ENTER_DEVICE(device);
   const size_t n = nq, N = plant == 0 ? 11 : 10, NIN = plant == 0 ? 9 : 8;
-  double *dx, *du;
-  int* ds;
-  CU(dalloc(&dx, n * N)); CU(dalloc(&du, n * NIN)); CU(dalloc(&ds, n));
-  CU(cudaMemcpy(dx, x, n * N * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(du, u, n * NIN * sizeof(double), cudaMemcpyHostToDevice));
+  DevBuf<double> dx, du;
+  DevBuf<int> ds;
+  CU(dx.upload(x, n * N)); CU(du.upload(u, n * NIN)); CU(ds.alloc(n));
   if (plant == 0)
-    plant_integrate_kernel<0><<<(nq + 3) / 4, 128>>>(nq, dx, du, Ts, ds);
+    plant_integrate_kernel<0><<<(nq + 3) / 4, 128>>>(nq, dx.p, du.p, Ts, ds.p);
   else
-    plant_integrate_kernel<1><<<(nq + 3) / 4, 128>>>(nq, dx, du, Ts, ds);
+    plant_integrate_kernel<1><<<(nq + 3) / 4, 128>>>(nq, dx.p, du.p, Ts, ds.p);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(x, dx, n * N * sizeof(double), cudaMemcpyDeviceToHost));
-  if (n_substeps) CU(cudaMemcpy(n_substeps, ds, n * sizeof(int), cudaMemcpyDeviceToHost));
-  cudaFree(dx); cudaFree(du); cudaFree(ds);
+  CU(dx.download(x, n * N));
+  if (n_substeps) CU(ds.download(n_substeps, n));
   return CMPC_OK;
 }
 

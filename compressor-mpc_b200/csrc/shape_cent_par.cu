@@ -1,0 +1,3 @@
+// Kernels and launch sequences of controller shape Shape<0, 3, 4, 1> (plant, n_y, n_u, n_controllers).
+#include "shape_ops.cuh"
+CMPC_DEFINE_SHAPE_OPS(kOps_cent_par, 0, 3, 4, 1)

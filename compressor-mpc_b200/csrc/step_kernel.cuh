@@ -1142,7 +1142,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 struct QpBounds4 {
   double lo0, lo1, up0, up1, rlo0, rlo1, rup0, rup1;
 };
-__device__ __noinline__ int qp_fallback4(const double* H, double f0, double f1, double f2, double f3, QpBounds4 b,
+static __device__ __noinline__ int qp_fallback4(const double* H, double f0, double f1, double f2, double f3, QpBounds4 b,
                                          unsigned* wset_out) {
   QpData<4> qd;
   qd.lb[0] = qd.lb[2] = b.lo0; qd.lb[1] = qd.lb[3] = b.lo1;
