@@ -148,6 +148,22 @@ class NerveCenter:
                                                 vp(block_end_ptr), vp(block_off_ptr), vp(traj_ptr),
                                                 vp(act_ptr), vp(obj_ptr), vp(st_ptr), vp(stream)))
 
+    def closed_loop_start(self, x0):
+        """Streaming closed loop with host I/O: place the scenarios at x0 (B, n_states)."""
+        x0 = f64(np.broadcast_to(f64(x0), (self.batch, self.n_states)))
+        check(lib().cmpc_closed_loop_start(self._h, ptr(x0)))
+
+    def closed_loop_step(self, plant_offset) -> np.ndarray:
+        """One sample: plant-input offsets (B, n_inputs) in, record [t, x, u, y] (B, 1+n+8) out."""
+        off = f64(np.broadcast_to(f64(plant_offset), (self.batch, self.n_inputs)))
+        rec = np.empty((self.batch, 1 + self.n_states + 8))
+        check(lib().cmpc_closed_loop_step(self._h, ptr(off), ptr(rec)))
+        return rec
+
+    def closed_loop_step_raw(self, offset_host_ptr: int, record_host_ptr: int):
+        """Same on raw host addresses (pinned buffers)."""
+        check(lib().cmpc_closed_loop_step(self._h, C.c_void_p(offset_host_ptr), C.c_void_p(record_host_ptr)))
+
     def set_timing(self, on: bool = True):
         check(lib().cmpc_set_timing(self._h, int(on)))
 

@@ -247,7 +247,8 @@ int cmpc_destroy(cmpc_handle* h) {
   DeviceState& G = h->G;
   void* ptrs[] = {G.ctrl, G.guess, G.scen, G.u_offset, G.work, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
                   G.active, G.objective, G.ticks, h->d_yref, h->d_y, h->d_u, h->d_xinit, h->d_uinit,
-                  h->d_uinitfull, h->d_yinit, h->d_x, h->d_ring, h->d_block_end, h->d_block_off};
+                  h->d_uinitfull, h->d_yinit, h->d_x, h->d_ring, h->d_block_end, h->d_block_off,
+                  h->d_step_end, h->d_step_off, h->d_rec};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -439,9 +440,10 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
   A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
   A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;
   A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
-  A.qp_status = qp_status_dev; A.n_steps = total_steps;
+  A.qp_status = qp_status_dev; A.n_steps = total_steps; A.rec_base = 0;
   const int rc = kShapeOps[h->shape]->closed_loop(h, first_step, n_steps, x0_dev, A, reinit,
                                                    static_cast<cudaStream_t>(stream));
+  h->stream_next = -1;   // a cmpc_closed_loop_start / _step sequence does not survive a run of this kind
   if (rc == CMPC_OK) {
     h->loop_next = first_step + n_steps;
     h->loop_total = total_steps;
@@ -453,6 +455,51 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
     h->loop_started = false;   // part of the launches may have gone out: the run cannot be continued
   }
   return rc;
+}
+
+int cmpc_closed_loop_start(cmpc_handle* h, const double* x0) {
+  CMPC_ENTER(h);
+  if (!x0) return fail(CMPC_ERR_ARG, "null argument");
+  const size_t B = h->cfg.batch;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h->d_xinit, x0, B * h->N * sizeof(double), cudaMemcpyHostToDevice));
+  if (!h->d_step_end) {
+    CU(dalloc(&h->d_step_end, B));
+    CU(dalloc(&h->d_step_off, B * h->NIN));
+    CU(dalloc(&h->d_rec, B * (1 + h->N + 8)));
+    std::vector<int> never(B, 0x7fffffff);   // a single block that never ends: the offsets of a sample are
+    CU(cudaMemcpy(h->d_step_end, never.data(), B * sizeof(int), cudaMemcpyHostToDevice));   // whatever the call brings
+  }
+  h->stream_next = 0;
+  h->loop_started = false;
+  return CMPC_OK;
+}
+
+int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* record) {
+  CMPC_ENTER(h);
+  if (!plant_offset || !record) return fail(CMPC_ERR_ARG, "null argument");
+  if (h->stream_next < 0) return fail(CMPC_ERR_STATE, "cmpc_closed_loop_start has not been called");
+  if (h->stream_next > 0 && !h->loop_started)
+    return fail(CMPC_ERR_STATE, "the controller was restarted since cmpc_closed_loop_start");
+  const size_t B = h->cfg.batch, REC = 1 + h->N + 8;
+  const int k = h->stream_next;
+  CU(cudaMemcpyAsync(h->d_step_off, plant_offset, B * h->NIN * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  ClosedLoopArrays A;
+  A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
+  A.block_end = h->d_step_end; A.block_off = h->d_step_off; A.n_blocks = 1;
+  A.traj = h->d_rec; A.qp_active = nullptr; A.qp_objective = nullptr; A.qp_status = nullptr;
+  A.n_steps = 1; A.rec_base = k;
+  if (int rc = kShapeOps[h->shape]->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) {
+    h->stream_next = -1;
+    h->loop_started = false;
+    return rc;
+  }
+  CU(cudaMemcpyAsync(record, h->d_rec, B * REC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream_next = k + 1;
+  h->loop_next = k + 1;
+  h->loop_total = -1;   // not a run the device-resident variant could continue
+  return CMPC_OK;
 }
 
 int cmpc_set_timing(cmpc_handle* h, int on) {

@@ -85,6 +85,10 @@ struct cmpc_handle {
   int* d_block_end = nullptr;
   double* d_block_off = nullptr;
   size_t block_cap = 0;
+  // closed loop one record per call with host I/O (cmpc_closed_loop_start / _step)
+  int* d_step_end = nullptr;
+  double *d_step_off = nullptr, *d_rec = nullptr;
+  int stream_next = -1;
   size_t smem_bytes = 0;
   int64_t launches = 0;
   bool initialized = false;

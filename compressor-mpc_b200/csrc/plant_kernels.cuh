@@ -205,7 +205,8 @@ struct ClosedLoopArrays {
   unsigned* qp_active; // [B][T][NCTRL] or null
   double* qp_objective;
   int* qp_status;
-  int n_steps;
+  int n_steps;         // records per scenario in traj / qp_* ...
+  int rec_base;        // ... whose slot 0 is record rec_base of the run
 };
 
 // Start of a closed-loop run: x = x0, y = GetOutput(x0), rings = 0.
@@ -249,7 +250,7 @@ __device__ __forceinline__ void advance_pair(int b, int c, unsigned pair_mask, i
   for (int i = 0; i < 5; ++i) xs[i] = A.x[size_t(b) * N + 5 * c + i];
   xs[5] = PLANT == 0 ? A.x[size_t(b) * N + (PLANT == 0 ? 10 : 0)] : 0.0;
   if (A.traj) {
-    double* r = A.traj + (size_t(b) * A.n_steps + k) * REC;
+    double* r = A.traj + (size_t(b) * A.n_steps + (k - A.rec_base)) * REC;
 #pragma unroll
     for (int i = 0; i < 5; ++i) r[1 + 5 * c + i] = xs[i];
     if (c == 0) {
@@ -263,7 +264,7 @@ __device__ __forceinline__ void advance_pair(int b, int c, unsigned pair_mask, i
     }
   }
   if (c < NCTRL) {
-    const size_t o = (size_t(b) * A.n_steps + k) * NCTRL + c;
+    const size_t o = (size_t(b) * A.n_steps + (k - A.rec_base)) * NCTRL + c;
     if (A.qp_active) A.qp_active[o] = active[b * NCTRL + c];
     if (A.qp_objective) A.qp_objective[o] = objective[b * NCTRL + c];
     if (A.qp_status) A.qp_status[o] = status[b * NCTRL + c];

@@ -131,6 +131,15 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
                                 const double* block_off_dev, double* traj_dev,
                                 uint32_t* qp_active_dev, double* qp_objective_dev,
                                 int32_t* qp_status_dev, void* stream);
+/* The same closed loop one record per call with HOST buffers: the body of the reference driver's
+ * loop (SimulationSystem::SetOffset -> ControllerInterface::GetNextInput ->
+ * SimulationSystem::SetInput -> Integrate, simulation_system.h:66-116).  cmpc_closed_loop_start
+ * places scenario b at x0[b] (B x n_states) with the controller initialised like the reference
+ * driver; every cmpc_closed_loop_step uploads this sample's plant-input offsets (B x n_inputs,
+ * added to the default input), runs the control step and the plant advance on the device and
+ * downloads the record [t, x, u, y] (B x (1+n_states+8)).  Blocking; runs on the handle's stream. */
+int cmpc_closed_loop_start(cmpc_handle* h, const double* x0);
+int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* record);
 /* Per-kernel device timing: when on, every control step (linearise [host-facing step only],
  * assemble, solve) is bracketed by CUDA events on its stream (which also keeps its kernels from
  * overlapping by dependent launch: use it to explain a run, not to time one); cmpc_get_timing synchronises, returns the

@@ -121,6 +121,10 @@ def test_control_step_matches_oracle(case, setups, pkg, gpu_lib):
             Ag, Bg, fdg = nc.linearization(c)
             Ao, Bo, Ado, Co, fdo = o.linearization(c)
             assert np.allclose(Ag[0], Ao, rtol=1e-11, atol=1e-14)
+            # the discretised B in this controller's input order: the reference keeps the undelayed
+            # columns in Borig and the delayed ones in Adelay (aug_lin_sys.cc:156-173)
+            assert np.allclose(Bg[0][:, [0, 2]], Bo, rtol=1e-10, atol=1e-15)
+            assert np.allclose(Bg[0][:, [1, 3]], Ado, rtol=1e-10, atol=1e-15)
             assert np.allclose(fdg[0], fdo, rtol=1e-10, atol=1e-15)
             Sug, Suog = nc.prediction(c)
             Suo_, _, _, Suoo = o.prediction(c)
@@ -706,3 +710,124 @@ def test_cxx_setup_driver_matches_reference_records(setups, golden, pkg, gpu_lib
     assert np.abs(got[:200, 11:15] - rec[:, 11:15]).max() < 1e-5
     # after record 200 the -0.1 offset on plant input 6 (second outlet valve) acts on its outlet pressure
     assert abs(got[-1, 7] - got[199, 7]) > 1e-3
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_full_recorded_run_on_gpu(case, setups, golden, pkg, gpu_lib):
+    """All 10 000 records of each of the reference's six recorded runs (results/*/run1), closed loop
+    on the GPU: through the disturbance at record 1001 to the end, within the print precision of the
+    .dat files (6 significant digits)."""
+    s = setups[case]
+    x_def, _ = ol.plant_defaults(s.plant)
+    T = int(golden[f"{case}/n_records"])
+    assert T == 10000
+    g = pkg.from_setup(s, batch=1).run_closed_loop(x_def, s.block_end_records(n_steps=T), s.sim_offsets, T)
+    idx, rec = golden[f"{case}/index"], golden[f"{case}/records"]
+    tr = g["traj"][0][idx]
+    n = len(x_def)
+    assert (g["status"] == 0).all()
+    assert np.allclose(tr[:, 0], rec[:, 0], rtol=1e-5, atol=1e-9)
+    assert (np.abs(tr[:, 1:1 + n] - rec[:, 1:1 + n]) / np.maximum(np.abs(rec[:, 1:1 + n]), 1e-3)).max() < 1e-5
+    assert np.abs(tr[:, 1 + n:5 + n] - rec[:, 1 + n:5 + n]).max() < 5e-6
+    assert (np.abs(tr[:, 5 + n:] - rec[:, 5 + n:]) / np.maximum(np.abs(rec[:, 5 + n:]), 1e-3)).max() < 1e-5
+
+
+def test_sweep_shape_at_size(setups, pkg, gpu_lib):
+    """BASELINE configs[4] shape at real occupancy: p = 200 (2 CTAs/SM, table behind the powers),
+    8192 scenarios, 300 records, against the oracle on a 64-scenario sample spread over the batch."""
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T, p = 8192, 300, 200
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = np.minimum(be[:, 0], 60 + (np.arange(B) % 200))     # the disturbance arrives inside the run
+    g = pkg.from_setup(s, batch=B, p=p).run_closed_loop(x0, be, bo, T)
+    n = len(x_def)
+    assert (g["status"] == 0).all() and np.isfinite(g["traj"]).all()
+    sample = np.unique(np.concatenate([np.arange(16), np.linspace(16, B - 1, 48).astype(int)]))
+    o = ol.Oracle(s, p=p).run_closed_loop(x0[sample], be[sample], bo[sample], T, n_threads=16)
+    u = g["traj"][:, :, 1 + n:5 + n]
+    assert rel_err(u[sample], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"][sample], o["active"])
+    assert rel_err(g["objective"][sample], o["objective"], 1e-6) < RTOL_U
+
+
+def test_headline_config_parity_protocol(setups, pkg, gpu_lib):
+    """coop-par x 4096 scenarios.  Scenarios 0..63 over the full run
+    and ALL 4096 scenarios over the first records, applied inputs / objectives / active sets against
+    the oracle.  The full protocol (10 000 and 1500 records: about 7 M oracle steps, minutes of host
+    time) runs with CMPC_FULL_PROTOCOL=1 (log in profiles/); the default sizes keep the suite short."""
+    import os
+    full = os.environ.get("CMPC_FULL_PROTOCOL") == "1"
+    T_long, T_all = (10000, 1500) if full else (2000, 120)
+    threads = os.cpu_count() or 1
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    n = len(x_def)
+    B = 4096
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T_long)
+    nc = pkg.from_setup(s, batch=64)
+    g = nc.run_closed_loop(x0[:64], be[:64], bo[:64], T_long)
+    o = ol.Oracle(s).run_closed_loop(x0[:64], be[:64], bo[:64], T_long, n_threads=threads)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+    nc.close()
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T_all)
+    if not full:
+        be[:, 0] = np.minimum(be[:, 0], 30 + (np.arange(B) % 60))   # every scenario meets its disturbance
+    g = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T_all)
+    o = ol.Oracle(s).run_closed_loop(x0, be, bo, T_all, n_threads=threads)
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
+    assert rel_err(g["objective"], o["objective"], 1e-6) < RTOL_U
+
+
+def test_streaming_closed_loop_with_host_buffers(setups, pkg, gpu_lib):
+    """cmpc_closed_loop_start / _step (one record per call, host buffers: bench.py's e2e path) gives
+    the records of cmpc_run_closed_loop bit for bit."""
+    s = setups["coop-ser"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 6, 70
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 20 + np.arange(B)
+    ref = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)["traj"]
+    nc = pkg.from_setup(s, batch=B)
+    with pytest.raises(pkg.capi.CmpcError, match="cmpc_closed_loop_start"):
+        nc.closed_loop_step(bo[:, 0])
+    nc.closed_loop_start(x0)
+    for k in range(T):
+        off = np.stack([bo[b, min(int((k >= be[b]).sum()), be.shape[1] - 1)] for b in range(B)])
+        rec = nc.closed_loop_step(off)
+        assert np.array_equal(rec, ref[:, k]), k
+
+
+def test_argument_validation_added_in_round_two(setups, pkg, gpu_lib):
+    import torch
+    s = setups["coop-par"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    nc = pkg.from_setup(s, batch=2)
+    lib, ptr, f64 = pkg.capi.lib(), pkg.capi.ptr, pkg.capi.f64
+    bad_uwt = f64([[1.0, 0.5], [0.25, 1.0]])
+    assert lib.cmpc_set_weights(nc._h, 0, ptr(bad_uwt), None) == 3        # CMPC_ERR_UNSUPPORTED: non-symmetric uwt
+    ok = f64([0.0, 0.0])
+    assert lib.cmpc_set_constraints(nc._h, 0, ptr(f64([0.5, 0.0])), ptr(ok), ptr(ok), ptr(ok)) == 1   # lower > upper
+    assert lib.cmpc_set_constraints(nc._h, 0, ptr(f64([np.nan, 0.0])), ptr(ok), ptr(ok), ptr(ok)) == 1
+    inf = f64([np.inf, np.inf])
+    assert lib.cmpc_set_constraints(nc._h, 0, ptr(-inf), ptr(inf), ptr(-inf), ptr(inf)) == 0            # unbounded is fine
+    # a continuation must pick up where the previous call stopped
+    B, T = 2, 20
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    dev = torch.device("cuda", 0)
+    d_x0, d_be, d_bo = (torch.from_numpy(a).to(dev) for a in (x0, be, bo))
+    d_traj = torch.zeros((B, T, 20), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    args = (d_x0.data_ptr(), be.shape[1], d_be.data_ptr(), d_bo.data_ptr(), d_traj.data_ptr(), 0, 0, 0, st)
+    nc.run_closed_loop_device(0, 5, T, *args)
+    with pytest.raises(pkg.capi.CmpcError, match="continuation does not match"):
+        nc.run_closed_loop_device(7, 1, T, *args)
+    with pytest.raises(pkg.capi.CmpcError, match="continuation does not match"):
+        nc.run_closed_loop_device(5, 1, T + 1, *args)
+    nc.run_closed_loop_device(5, 15, T, *args)
+    torch.cuda.synchronize()
+    assert torch.isfinite(d_traj).all()
+    assert torch.cuda.current_device() == 0

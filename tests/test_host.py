@@ -108,27 +108,40 @@ def _gloo_worker(rank, world, port, out_dir):
     sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
     import json
     import __graft_entry__ as entry
+    import bench
     import oracle_lib as ol2
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pkg = entry.load_package()
     s = pkg.setupfile.setup_from_dict(json.loads((ROOT / "tests/golden/setups.json").read_text())["coop-par"])
     x_def, _ = ol2.plant_defaults(0)
-    B, T = 3, 25
-    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T, first=rank * B)
-    tr = ol2.Oracle(s).run_closed_loop(x0, be, bo, T)["traj"]
-    last = torch.from_numpy(np.ascontiguousarray(tr[:, -1, :]))
-    gathered = [torch.empty_like(last) for _ in range(world)]
-    dist.all_gather(gathered, last)                 # the only collective of the N>1 path
+    first, B = bench.sweep_shard(6, world, rank)      # the sweep's strong-scaling shard rule
+    T = 25
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T, first=first)
+    res = ol2.Oracle(s).run_closed_loop(x0, be, bo, T)
+    traj = torch.from_numpy(np.ascontiguousarray(res["traj"]))
+    # bench.py's collective: the whole trajectory tensor, a chunk of records per all-gather
+    full = torch.zeros((world * B, T, traj.shape[2]), dtype=torch.float64)
+
+    def sink(k0, out):
+        full[:, k0:k0 + out.shape[2]] = out.reshape(world * B, out.shape[2], out.shape[3])
+    calls, n_rec = bench.chunked_all_gather(torch, dist, world, traj, 8, sink)
+    # health counters over all ranks (bench.py Dist.reduce): failures summed, finiteness and-ed, time max-ed
+    fails = torch.tensor([float((res["status"] != 0).sum() + rank)])
+    dist.all_reduce(fails, op=dist.ReduceOp.SUM)
+    finite = torch.tensor([1.0 if rank == 0 else 0.0])
+    dist.all_reduce(finite, op=dist.ReduceOp.MIN)
     t_max = torch.tensor([float(rank + 1)])
     dist.all_reduce(t_max, op=dist.ReduceOp.MAX)    # max-over-ranks timing reduction
     if rank == 0:
-        np.save(os.path.join(out_dir, "gathered.npy"), torch.cat(gathered).numpy())
-        np.save(os.path.join(out_dir, "tmax.npy"), t_max.numpy())
+        np.save(os.path.join(out_dir, "gathered.npy"), full.numpy())
+        np.save(os.path.join(out_dir, "scalars.npy"), np.array([t_max.item(), fails.item(), finite.item(), calls, n_rec]))
     dist.destroy_process_group()
 
 
 def test_two_rank_shard_and_gather_gloo(pkg, setups, tmp_path):
+    """The N > 1 host logic of bench.py on two CPU ranks: shard rule, chunked all-gather of the
+    trajectory tensor in global scenario order, all-reduced health counters."""
     import torch.multiprocessing as mp
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
@@ -136,9 +149,13 @@ def test_two_rank_shard_and_gather_gloo(pkg, setups, tmp_path):
     s = setups["coop-par"]
     x_def, _ = ol.plant_defaults(0)
     x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, 6, 25)
-    ref = ol.Oracle(s).run_closed_loop(x0, be, bo, 25)["traj"][:, -1, :]
-    assert np.array_equal(got, ref)
-    assert np.load(tmp_path / "tmax.npy")[0] == 2.0
+    ref = ol.Oracle(s).run_closed_loop(x0, be, bo, 25)["traj"]
+    assert np.array_equal(got[:, :24], ref[:, :24])      # 3 chunks of 8 records
+    assert (got[:, 24] == 0).all()                       # the ragged tail is not gathered
+    t_max, fails, finite, calls, n_rec = np.load(tmp_path / "scalars.npy")
+    assert (t_max, fails, finite, calls, n_rec) == (2.0, 1.0, 0.0, 3.0, 24.0)
+    import bench
+    assert [bench.sweep_shard(65536, 8, r) for r in (0, 7)] == [(0, 8192), (57344, 8192)]
 
 
 def test_dat_record_format_roundtrip(pkg, golden):

@@ -6,10 +6,8 @@ import pytest
 import oracle_lib as ol
 from conftest import CASES
 
-# full 10 000 records for the headline config, shorter prefixes for the others so that the
-# whole CPU suite stays within a few minutes; every prefix covers the disturbance onset.
-N_RECORDS = {"coop-par": 10000, "cent-ser": 10000, "coop-ser": 2600, "ncoop-par": 2600,
-             "cent-par": 2600, "ncoop-ser": 2600}
+# all 10 000 records of every recorded run (about 10 s of oracle time each)
+N_RECORDS = {case: 10000 for case in CASES}
 
 
 @pytest.mark.parametrize("case", CASES)
