@@ -46,6 +46,34 @@ int find_shape(const cmpc_config& c) {
   return -1;
 }
 
+// Room for the four window events of n_steps control steps, starting at win_used = 0.
+int reserve_window_events(cmpc_handle* h, size_t n_steps) {
+  const size_t old = h->win_ev.size();
+  if (old < 4 * n_steps) {
+    h->win_ev.resize(4 * n_steps);
+    for (size_t i = old; i < h->win_ev.size(); ++i) {
+      cudaError_t e = cudaEventCreate(&h->win_ev[i]);
+      if (e != cudaSuccess) {
+        h->win_ev.resize(i);
+        return fail(CMPC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+      }
+    }
+  }
+  h->win_used = 0;
+  return CMPC_OK;
+}
+
+// Measured time of control step i of the last windowed run, in nanoseconds.
+int window_ns(cmpc_handle* h, size_t i, int64_t* ns) {
+  float a = 0.f, b = 0.f;
+  cudaEvent_t* w = &h->win_ev[4 * i];
+  cudaError_t e = cudaEventElapsedTime(&a, w[0], w[1]);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&b, w[2], w[3]);
+  if (e != cudaSuccess) return fail(CMPC_ERR_CUDA, std::string("cudaEventElapsedTime: ") + cudaGetErrorString(e));
+  *ns = int64_t((double(a) + double(b)) * 1e6 + 0.5);
+  return CMPC_OK;
+}
+
 // StepParams::obs_states_free: do the observer gains leave the plant-state estimates alone?
 void update_obs_states_free(cmpc_handle* h) {
   bool free_ = true;
@@ -252,6 +280,7 @@ int cmpc_destroy(cmpc_handle* h) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->win_ev) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CMPC_OK;
@@ -389,6 +418,28 @@ int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
   CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return CMPC_OK;
+}
+
+int cmpc_get_next_input_timed(cmpc_handle* h, const double* y, double* u, int n_timing_iterations,
+                              int64_t* time_ns) {
+  CMPC_ENTER(h);
+  if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
+  if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
+  if (!y || !u || !time_ns) return fail(CMPC_ERR_ARG, "null argument");
+  if (int rc = reserve_window_events(h, 1)) return rc;
+  const size_t bytes = size_t(h->cfg.batch) * 4 * sizeof(double);
+  cudaEvent_t* w = h->win_ev.data();
+  CU(cudaEventRecord(w[0], h->stream));
+  CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->window_on = true;
+  h->window_n = n_timing_iterations;
+  int rc = kShapeOps[h->shape]->step(h, h->d_y, h->d_u, h->stream);
+  h->window_on = false;
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(w[3], h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return window_ns(h, 0, time_ns);
 }
 
 int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double* objective) {
@@ -530,9 +581,19 @@ int cmpc_get_timing(cmpc_handle* h, int64_t* n_steps, double* step_ms, double* a
 int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
                          const int32_t* block_end, const double* block_off, double* traj,
                          uint32_t* qp_active, double* qp_objective, int32_t* qp_status) {
+  return cmpc_run_closed_loop_timed(h, n_steps, x0, n_blocks, block_end, block_off, traj, qp_active, qp_objective,
+                                    qp_status, -1, nullptr);
+}
+
+int cmpc_run_closed_loop_timed(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
+                               const int32_t* block_end, const double* block_off, double* traj,
+                               uint32_t* qp_active, double* qp_objective, int32_t* qp_status,
+                               int n_timing_iterations, int64_t* step_ns) {
   CMPC_ENTER(h);
   if (!x0 || !block_end || !block_off || n_blocks < 1 || n_steps < 0)
     return fail(CMPC_ERR_ARG, "bad closed-loop arguments");
+  if (step_ns)
+    if (int rc = reserve_window_events(h, size_t(n_steps))) return rc;
   const size_t B = h->cfg.batch, NC = h->NCTRL, REC = 1 + h->N + 8;
   for (size_t b = 0; b < B; ++b)
     for (int i = 0; i < n_blocks; ++i) {
@@ -562,10 +623,15 @@ int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_bl
   if (qp_active) CU(d_act.alloc(nrec * NC));
   if (qp_objective) CU(d_obj.alloc(nrec * NC));
   if (qp_status) CU(d_st.alloc(nrec * NC));
-  if (int rc = cmpc_run_closed_loop_device(h, 0, n_steps, n_steps, h->d_xinit, n_blocks, h->d_block_end,
-                                           h->d_block_off, d_traj.p, d_act.p, d_obj.p, d_st.p, h->stream))
-    return rc;
+  h->window_on = step_ns != nullptr;
+  h->window_n = n_timing_iterations;
+  const int rc_run = cmpc_run_closed_loop_device(h, 0, n_steps, n_steps, h->d_xinit, n_blocks, h->d_block_end,
+                                                 h->d_block_off, d_traj.p, d_act.p, d_obj.p, d_st.p, h->stream);
+  h->window_on = false;
+  if (rc_run) return rc_run;
   CU(cudaStreamSynchronize(h->stream));
+  for (int k = 0; step_ns && k < n_steps; ++k)
+    if (int rc = window_ns(h, size_t(k), &step_ns[k])) return rc;
   if (traj) CU(d_traj.download(traj, nrec * REC));
   if (qp_active) CU(d_act.download(qp_active, nrec * NC));
   if (qp_objective) CU(d_obj.download(qp_objective, nrec * NC));

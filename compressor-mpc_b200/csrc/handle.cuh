@@ -102,6 +102,13 @@ struct cmpc_handle {
   cudaStream_t stream = nullptr;   // the handle's own (non-blocking) stream: host-pointer entry points run on it
   std::vector<cudaEvent_t> ev;   // pairs (start, stop) around control-step launches
   size_t ev_used = 0;
+  // timing window of the reference's GetNextInputWithTiming (n-timing-iterations): four events per
+  // control step [start, end of the timed sweeps, start of what follows the sweeps, end]; the
+  // caller of launch_step records the outer two
+  bool window_on = false;
+  int window_n = -1;
+  std::vector<cudaEvent_t> win_ev;
+  size_t win_used = 0;
 };
 
 namespace cmpc {

@@ -99,7 +99,28 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
   CU(launch_pdl(assemble_variant<S>(h->cfg.p), B, S::NCTRL * S::TPC, h->smem_bytes, st, h->P, h->G, y));
   if (ev) CU(cudaEventRecord(ev[2], st));
   // K2: Jacobi sweeps + update; one lane pair per scenario
-  CU(launch_pdl(solve_kernel<S>, (B * S::NCTRL + 63) / 64, 64, 0, st, h->P, h->G, u));
+  const unsigned solve_grid = (B * S::NCTRL + 63) / 64;
+  if (h->window_on && h->window_n >= 0 && h->window_n < h->P.n_iter) {
+    // timing window (nerve_center.h:150-159): the sweeps from n_timing_iterations on are left out
+    // of the measured time, what follows the sweeps is measured again
+    cudaEvent_t* w = &h->win_ev[h->win_used];
+    const int n_t = h->window_n;
+    if (n_t > 0) {
+      solve_sweeps_kernel<S><<<solve_grid, 64, 0, st>>>(h->P, h->G, 0, n_t);
+      h->launches++;
+    }
+    CU(cudaEventRecord(w[1], st));
+    solve_sweeps_kernel<S><<<solve_grid, 64, 0, st>>>(h->P, h->G, n_t, h->P.n_iter);
+    CU(cudaEventRecord(w[2], st));
+    solve_finish_kernel<S><<<solve_grid, 64, 0, st>>>(h->P, h->G, u);
+    h->launches++;
+  } else {
+    CU(launch_pdl(solve_kernel<S>, solve_grid, 64, 0, st, h->P, h->G, u));
+    if (h->window_on) {   // the window is the whole step: the two inner events coincide
+      CU(cudaEventRecord(h->win_ev[h->win_used + 1], st));
+      CU(cudaEventRecord(h->win_ev[h->win_used + 2], st));
+    }
+  }
   h->P.ring_pos = (h->P.ring_pos + 1) % kRing;   // the oldest ring slot was consumed and refilled
   if (ev) CU(cudaEventRecord(ev[3], st));
   h->launches += 2;
@@ -123,8 +144,13 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
   double t = 0.0;
   for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;  // the reference driver accumulates t += Ts
   for (int k = first_step; k < first_step + n_steps; ++k) {
+    if (h->window_on) CU(cudaEventRecord(h->win_ev[h->win_used], st));
     int rc = launch_step<S>(h, A.y, A.u, st);
     if (rc) return rc;
+    if (h->window_on) {
+      CU(cudaEventRecord(h->win_ev[h->win_used + 3], st));
+      h->win_used += 4;
+    }
     // plant side of record k, and the observer update + linearisation of record k + 1
     CU(launch_pdl(cl_advance_kernel<S>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
     h->lin_ahead = true;

@@ -57,6 +57,9 @@ constexpr int kScenStateStride = 16;   // doubles per scenario
 constexpr int kWorkStride = 512, kWAc = 0, kWXc = 144, kWCc = 288, kWBF = 336;
 // kWBF holds what the a-priori observer update needs: base[N] (free response of the state part),
 // then the Bd columns of the undelayed inputs 0 and 2 (N each)
+// kWPlan: hand-over between the launches of a solve that is split for the timing window
+// (n-timing-iterations): the plan (up to 8), the working set, the status of the last sweep
+constexpr int kWPlan = 384, kWPlanSet = 392;
 constexpr int kRing = kDelay - 1;   // slots of one delay ring (the head is kept separately)
 constexpr int kMaxStageTilesLadder = 18;  // squaring (2) + up to 16 blocks x 6 columns / 8 per giant-step stage
 constexpr int kMaxPow = 8;           // stages of the power ladder: horizons up to 8 * 2^5 = 256
@@ -1190,11 +1193,14 @@ __device__ __forceinline__ void apriori_update(const StepParams& P, const Device
 #ifndef CMPC_SOLVE_MIN_BLOCKS
 #define CMPC_SOLVE_MIN_BLOCKS 1
 #endif
-template <class S>
-__global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
-solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
-  pdl_wait();
-  pdl_trigger();   // single wave
+// MODE 0: the whole of it (the production path).  The other two exist for the reference's timing
+// window (GetNextInputWithTiming, nerve_center.h:134-179: sweeps i >= n_timing_iterations are left
+// out of the measured time): MODE 1 runs sweeps [it_begin, it_end) and parks plan, working set and
+// status in the hand-over record; MODE 2 is what follows the sweeps (first move, UpdateU /
+// ObserveAPriori).  Sweeps 0..n-1 followed by n..n_iter-1 and MODE 2 leave exactly the state MODE 0 does.
+template <class S, int MODE>
+__device__ __forceinline__ void solve_body(const StepParams& P, const DeviceState& G, double* __restrict__ u,
+                                           int it_begin, int it_end) {
   constexpr int NU = S::NU, NV = S::NV, NVO = S::NVO, NCTRL = S::NCTRL;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (NV == 4 && NCTRL == 2) {
@@ -1203,6 +1209,22 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     const unsigned pm = 3u << (threadIdx.x & 30);   // the two lanes of this scenario
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen) * 2 + c;
+    double* plan = G.work + rec * kWorkStride + kWPlan;
+    if constexpr (MODE == 2) {
+      double zf[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) zf[k] = plan[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ss[4 + c * 4 + k] = zf[k];
+      const double un0 = ss[2 * c] + zf[0], un1 = ss[2 * c + 1] + zf[1];
+      ss[2 * c] = un0;
+      ss[2 * c + 1] = un1;
+      u[size_t(scen) * 4 + 2 * c] = un0;
+      u[size_t(scen) * 4 + 2 * c + 1] = un1;
+      const double duf[4] = {zf[0], zf[1], 0.0, 0.0};
+      apriori_update<S>(P, G, rec, duf);
+      return;
+    }
     const double* gH = G.qpH + rec * 16;
     const double* gf = G.qpf + rec * 4;
     const double* gG = G.qpG + rec * 16;
@@ -1211,7 +1233,7 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       f0[i] = gf[i];
-      z[i] = ss[4 + c * 4 + i];          // du_prev = du_old_ (own plan)
+      z[i] = (MODE == 1 && it_begin > 0) ? plan[i] : ss[4 + c * 4 + i];   // du_prev = du_old_ (own plan)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         Hm[i][j] = gH[i * 4 + j];
@@ -1229,13 +1251,15 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
       bnd[12 + i] = -P.c[c].rate_upper[i & 1];
     }
     unsigned wset = G.guess[rec];
+    if (MODE == 1 && it_begin > 0) wset = unsigned(__double_as_longlong(plan[kWPlanSet - kWPlan]));
     if (wset == kQpNoGuess) wset = 0;     // no warm start: begin from the unconstrained minimiser
     const bool pd = qt_inverse(J);
     QtReduced red;
     bool red_ok = false, need_prep = true;   // red belongs to wset once prepared
     double x[4] = {0.0, 0.0, 0.0, 0.0}, lam[4] = {0.0, 0.0, 0.0, 0.0}, fi[4] = {0.0, 0.0, 0.0, 0.0};
     int status = pd ? 0 : 3;
-    for (int it = 0; it < P.n_iter; ++it) {
+    const int it_lo = MODE == 1 ? it_begin : 0, it_hi = MODE == 1 ? it_end : P.n_iter;
+    for (int it = it_lo; it < it_hi; ++it) {
       double zo[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) zo[k] = __shfl_xor_sync(pm, z[k], 1);   // the other controller's previous plan
@@ -1308,21 +1332,27 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
       m &= m - 1;
       if (idx >= 0 && lam[w] > 1e-9 * fmax) act |= 1u << idx;
     }
-    if (status == 0) G.guess[rec] = wset;
+    if (status == 0 && (MODE == 0 || it_end == P.n_iter)) G.guess[rec] = wset;
     G.status[rec] = status;
     G.active[rec] = status == 0 ? act : 0u;
     G.objective[rec] = status == 0 ? obj : 0.0;
-    // du_old_ = du_prev; u_old_ += first move of each controller's plan (system order = ctrl 0, ctrl 1)
+    if constexpr (MODE == 1) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ss[4 + c * 4 + k] = z[k];
-    const double un0 = ss[2 * c] + z[0], un1 = ss[2 * c + 1] + z[1];
-    ss[2 * c] = un0;
-    ss[2 * c + 1] = un1;
-    u[size_t(scen) * 4 + 2 * c] = un0;
-    u[size_t(scen) * 4 + 2 * c + 1] = un1;
-    // each controller sees only its own inputs move (nerve_center.h:322-328)
-    const double du[4] = {z[0], z[1], 0.0, 0.0};
-    apriori_update<S>(P, G, rec, du);
+      for (int k = 0; k < 4; ++k) plan[k] = z[k];
+      plan[kWPlanSet - kWPlan] = __longlong_as_double((long long)wset);
+    } else {
+      // du_old_ = du_prev; u_old_ += first move of each controller's plan (system order = ctrl 0, ctrl 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ss[4 + c * 4 + k] = z[k];
+      const double un0 = ss[2 * c] + z[0], un1 = ss[2 * c + 1] + z[1];
+      ss[2 * c] = un0;
+      ss[2 * c + 1] = un1;
+      u[size_t(scen) * 4 + 2 * c] = un0;
+      u[size_t(scen) * 4 + 2 * c + 1] = un1;
+      // each controller sees only its own inputs move (nerve_center.h:322-328)
+      const double du[4] = {z[0], z[1], 0.0, 0.0};
+      apriori_update<S>(P, G, rec, du);
+    }
   } else {
     // centralised controller: a single controller has no plan to exchange, every sweep solves the
     // same QP (distributed_controller.h:215-218), so one solve gives the result of all sweeps
@@ -1331,6 +1361,24 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     if (scen >= P.batch) return;
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen);
+    double* plan = G.work + rec * kWorkStride + kWPlan;
+    if constexpr (MODE == 1) {
+      if (it_begin > 0 || it_end <= it_begin) return;   // every sweep solves the same QP: the first one has the answer
+    }
+    if constexpr (MODE == 2) {
+      double du[4];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) ss[4 + i] = plan[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        du[k] = plan[k];
+        const double un = ss[k] + du[k];
+        ss[k] = un;
+        u[size_t(scen) * 4 + k] = un;
+      }
+      apriori_update<S>(P, G, rec, du);
+      return;
+    }
     const double* gH = G.qpH + rec * NV * NV;
     const double* gf = G.qpf + rec * NV;
     const double* uo = G.ctrl + rec * kCtrlStateStride + kOffUold;
@@ -1358,18 +1406,43 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
     G.status[rec] = status;
     G.active[rec] = status == 0 ? act : 0u;
     G.objective[rec] = status == 0 ? obj : 0.0;
-    double du[4];
+    if constexpr (MODE == 1) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) ss[4 + i] = z[i];
+      for (int i = 0; i < NV; ++i) plan[i] = z[i];
+    } else {
+      double du[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      du[k] = z[k];
-      const double un = ss[k] + z[k];
-      ss[k] = un;
-      u[size_t(scen) * 4 + k] = un;
+      for (int i = 0; i < NV; ++i) ss[4 + i] = z[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        du[k] = z[k];
+        const double un = ss[k] + z[k];
+        ss[k] = un;
+        u[size_t(scen) * 4 + k] = un;
+      }
+      apriori_update<S>(P, G, rec, du);
     }
-    apriori_update<S>(P, G, rec, du);
   }
+}
+
+template <class S>
+__global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
+solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+  pdl_wait();
+  pdl_trigger();   // single wave
+  solve_body<S, 0>(P, G, u, 0, 0);
+}
+
+// The same in pieces, for the timing window only.
+template <class S>
+__global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
+solve_sweeps_kernel(StepParams P, DeviceState G, int it_begin, int it_end) {
+  solve_body<S, 1>(P, G, nullptr, it_begin, it_end);
+}
+template <class S>
+__global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
+solve_finish_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+  solve_body<S, 2>(P, G, u, 0, 0);
 }
 
 }  // namespace cmpc

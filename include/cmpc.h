@@ -97,6 +97,13 @@ int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
  * has already consumed the next measurement (its plant kernel runs the observer update and the
  * linearisation of the following record), so the handle needs cmpc_initialize first. */
 int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u);
+/* NerveCenter::GetNextInputWithTiming (nerve_center.h:134-182): the same step; *time_ns gets the
+ * time of what the reference's timer covers, measured with CUDA events on the handle's stream: the
+ * copy of y, QP generation, the first n_timing_iterations sweeps and, after the remaining sweeps
+ * (not measured, nerve_center.h:151), everything that follows them (first move, a-priori observer
+ * update, copy of u).  n_timing_iterations < 0 or >= n_iterations: the whole call. */
+int cmpc_get_next_input_timed(cmpc_handle* h, const double* y, double* u, int n_timing_iterations,
+                              int64_t* time_ns);
 /* Same with device-resident y/u (B x 4 doubles each) on `stream` (a cudaStream_t), no sync. */
 int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_dev, void* stream);
 
@@ -121,6 +128,14 @@ int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double
 int cmpc_run_closed_loop(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
                          const int32_t* block_end, const double* block_off, double* traj,
                          uint32_t* qp_active, double* qp_objective, int32_t* qp_status);
+/* The same run with the reference's timing window around the control step of every record (the
+ * setup key n-timing-iterations; what the *-with-timing programs write as the last value of a
+ * record): step_ns n_steps values, one per record for the whole batch (CUDA events; the plant side
+ * of the loop is not part of it, as in the reference).  step_ns NULL: cmpc_run_closed_loop. */
+int cmpc_run_closed_loop_timed(cmpc_handle* h, int n_steps, const double* x0, int n_blocks,
+                               const int32_t* block_end, const double* block_off, double* traj,
+                               uint32_t* qp_active, double* qp_objective, int32_t* qp_status,
+                               int n_timing_iterations, int64_t* step_ns);
 /* Device-resident variant: same arrays in device memory, runs on `stream`, no sync.
  * Runs records [first_step, first_step + n_steps) of a run whose arrays hold total_steps
  * records per scenario; first_step == 0 (re)starts the scenarios from x0_dev, later calls
