@@ -109,6 +109,15 @@ class NerveCenter:
         check(lib().cmpc_get_next_input(self._h, ptr(y), ptr(u)))
         return u
 
+    def GetNextInputWithTiming(self, y, n_timing_iterations: int = -1):
+        """NerveCenter::GetNextInputWithTiming (nerve_center.h:134-182): returns (u, time_ns), the time
+        covering QP generation, the first n_timing_iterations sweeps and what follows the sweeps."""
+        y = f64(np.broadcast_to(f64(y), (self.batch, 4)))
+        u = np.empty((self.batch, 4))
+        ns = C.c_int64()
+        check(lib().cmpc_get_next_input_timed(self._h, ptr(y), ptr(u), int(n_timing_iterations), C.byref(ns)))
+        return u, ns.value
+
     def GetNextInputRaw(self, y_host_ptr: int, u_host_ptr: int):
         """Same call on raw host addresses (e.g. pinned torch tensors): B x 4 doubles each."""
         check(lib().cmpc_get_next_input(self._h, C.c_void_p(y_host_ptr), C.c_void_p(u_host_ptr)))
@@ -125,7 +134,10 @@ class NerveCenter:
         return dict(status=st.reshape(shp), active=act.reshape(shp), objective=obj.reshape(shp))
 
     # ---- closed loop --------------------------------------------------------------------
-    def run_closed_loop(self, x0, block_end, block_off, n_steps, want_traj=True, want_qp=True):
+    def run_closed_loop(self, x0, block_end, block_off, n_steps, want_traj=True, want_qp=True,
+                        n_timing_iterations=None):
+        """n_timing_iterations given: the result also holds step_ns (n_steps,), the reference's timing
+        window around the control step of every record (cmpc_run_closed_loop_timed)."""
         B = self.batch
         x0 = f64(np.broadcast_to(f64(x0), (B, self.n_states)))
         block_end = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(block_end), (B, np.atleast_2d(block_end).shape[1])), dtype=np.int32)
@@ -136,9 +148,14 @@ class NerveCenter:
         act = np.zeros((B, n_steps, self.n_controllers), dtype=np.uint32) if want_qp else None
         obj = np.zeros((B, n_steps, self.n_controllers)) if want_qp else None
         st = np.zeros((B, n_steps, self.n_controllers), dtype=np.int32) if want_qp else None
-        check(lib().cmpc_run_closed_loop(self._h, n_steps, ptr(x0), nb, ptr(block_end), ptr(block_off),
-                                         ptr(traj), ptr(act), ptr(obj), ptr(st)))
-        return dict(traj=traj, active=act, objective=obj, status=st)
+        if n_timing_iterations is None:
+            check(lib().cmpc_run_closed_loop(self._h, n_steps, ptr(x0), nb, ptr(block_end), ptr(block_off),
+                                             ptr(traj), ptr(act), ptr(obj), ptr(st)))
+            return dict(traj=traj, active=act, objective=obj, status=st)
+        ns = np.zeros(n_steps, dtype=np.int64)
+        check(lib().cmpc_run_closed_loop_timed(self._h, n_steps, ptr(x0), nb, ptr(block_end), ptr(block_off),
+                                               ptr(traj), ptr(act), ptr(obj), ptr(st), int(n_timing_iterations), ptr(ns)))
+        return dict(traj=traj, active=act, objective=obj, status=st, step_ns=ns)
 
     def run_closed_loop_device(self, first_step, n_steps, total_steps, x0_ptr, n_blocks, block_end_ptr,
                                block_off_ptr, traj_ptr=0, act_ptr=0, obj_ptr=0, st_ptr=0, stream=0):

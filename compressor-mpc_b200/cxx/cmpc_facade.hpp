@@ -102,6 +102,13 @@ class NerveCenter : public ControllerInterface {
     Check(cmpc_initialize(h_, x_init, u_init, u_init_full, y_init));
   }
   void GetNextInput(const double* y, double* u) override { Check(cmpc_get_next_input(h_, y, u)); }
+  /// nerve_center.h:134-182: the time covers QP generation, the first n_timing_iterations sweeps
+  /// and what follows the sweeps (boost::timer::nanosecond_type is a 64-bit integer)
+  void GetNextInputWithTiming(const double* y, double* u, int n_timing_iterations = -1, int64_t* time_out = nullptr) {
+    int64_t ns = 0;
+    Check(cmpc_get_next_input_timed(h_, y, u, n_timing_iterations, &ns));
+    if (time_out) *time_out = ns;
+  }
 
 #ifdef CMPC_HAVE_EIGEN
   template <int N>

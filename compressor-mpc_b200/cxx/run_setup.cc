@@ -38,7 +38,7 @@ int main(int argc, char** argv) {
     SetupReader rd(argv[1]);
     double v[64];
     rd.ExpectKey("n-iterations"); rd.ReadNumbers(v, 1); const int n_iter = int(v[0]);
-    rd.ExpectKey("n-timing-iterations"); rd.ReadNumbers(v, 1);
+    rd.ExpectKey("n-timing-iterations"); rd.ReadNumbers(v, 1); const int n_timing = int(v[0]);
     rd.ExpectKey("folder-name"); const std::string folder = rd.ReadString();
     rd.ExpectKey("output-filename"); const std::string fname = rd.ReadString();
     NerveCenter nc(plant, mode, n_iter, batch);
@@ -91,12 +91,13 @@ int main(int argc, char** argv) {
       std::copy(block_end.begin(), block_end.end(), be.begin() + size_t(b) * nb);
     }
     std::vector<double> traj(size_t(batch) * T * rec);
-    Check(cmpc_set_timing(nc.handle(), 1));
-    Check(cmpc_run_closed_loop(nc.handle(), T, x0.data(), nb, be.data(), bo.data(), traj.data(), nullptr, nullptr, nullptr));
-    int64_t n_timed = 0;
-    double step_ms = 0, asm_ms = 0;
-    Check(cmpc_get_timing(nc.handle(), &n_timed, &step_ms, &asm_ms));
-    const long long ns = n_timed ? (long long)(step_ms / n_timed * 1e6) : 0;
+    // every record carries the time of its own control step inside the reference's timing window
+    // (GetNextInputWithTiming(y, n_timing_iterations, &time), nerve_center.h:134-182)
+    std::vector<int64_t> step_ns(T);
+    Check(cmpc_run_closed_loop_timed(nc.handle(), T, x0.data(), nb, be.data(), bo.data(), traj.data(), nullptr, nullptr,
+                                     nullptr, n_timing, step_ns.data()));
+    double mean_ns = 0;
+    for (int r = 0; r < T; ++r) mean_ns += double(step_ns[r]) / T;
     std::ofstream out(folder + "/" + fname);
     if (!out) throw std::runtime_error("cannot write " + folder + "/" + fname + " (does the folder exist?)");
     for (int r = 0; r < T; ++r) {
@@ -104,10 +105,10 @@ int main(int argc, char** argv) {
       char tb[32];
       std::snprintf(tb, sizeof tb, "%g", q[0]);
       out << tb << "\n" << FormatRow(q + 1, n) << "\n" << FormatRow(q + 1 + n, 4) << "\n" << FormatRow(q + 5 + n, 4)
-          << "\n" << ns << "\n\n";
+          << "\n" << (long long)step_ns[r] << "\n\n";
     }
     std::printf("%d records x %d scenario(s) -> %s/%s, %.1f us per batched control step\n", T, batch, folder.c_str(),
-                fname.c_str(), ns / 1e3);
+                fname.c_str(), mean_ns / 1e3);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -88,26 +88,105 @@ def run_setup(setup_path, plant=None, mode=None, batch=1, out_dir=None, n_record
     x_def, _ = capi.plant_defaults(plant)
     x0, be, bo = scenarios.make_scenarios(s, x_def, batch, T, Ts=Ts)
     nc = controller.from_setup(s, batch=batch, device=device)
-    nc.set_timing(True)
     t0 = time.perf_counter()
-    res = nc.run_closed_loop(x0, be, bo, T, want_qp=True)
+    # every record carries the time of its own control step inside the reference's timing window
+    # (GetNextInputWithTiming with the setup's n-timing-iterations, nerve_center.h:134-182)
+    res = nc.run_closed_loop(x0, be, bo, T, want_qp=True, n_timing_iterations=s.n_timing_iterations)
     wall = time.perf_counter() - t0
-    n_timed, step_ms, _ = nc.get_timing()
-    ns_per_step = step_ms / max(n_timed, 1) * 1e6       # mean device time of one (batched) control step
+    step_ns = res["step_ns"]
     out_dir = pathlib.Path(out_dir if out_dir is not None else s.folder_name)
     out_dir.mkdir(parents=True, exist_ok=True)
     n = len(x_def)
     paths = []
     for b in range(batch):
         p = out_dir / (s.output_filename if b == 0 else f"{s.output_filename}.s{b}")
-        p.write_text(format_records(res["traj"][b], n, ns_per_step))
+        p.write_text(format_records(res["traj"][b], n, step_ns))
         paths.append(p)
-    return dict(paths=paths, result=res, ns_per_step=ns_per_step, wall_s=wall, setup=s)
+    nc.close()
+    return dict(paths=paths, result=res, step_ns=step_ns, ns_per_step=float(step_ns.mean()) if T else 0.0,
+                wall_s=wall, setup=s)
+
+
+# setup/run-all-tests.sh:6-35: the two centralised runs, then for i = 1..9 the four distributed ones
+# with n-timing-iterations = i written to coop<i>.dat / ncoop<i>.dat
+ALL_TESTS_CENT = [("setup-cent-par", "parallel", "centralized"), ("setup-cent-ser", "serial", "centralized")]
+ALL_TESTS_DIST = [("setup-coop-par", "parallel", "cooperative", "coop"), ("setup-coop-ser", "serial", "cooperative", "coop"),
+                  ("setup-ncoop-par", "parallel", "noncoop", "ncoop"), ("setup-ncoop-ser", "serial", "noncoop", "ncoop")]
+
+
+def set_setup_params(text: str, n_timing_iterations: int, filename: str) -> str:
+    """The two gawk edits of setup/run-all-tests.sh:39-47: the line after the n-timing-iterations key
+    and the line after the output-filename key are replaced."""
+    out, pending = [], None
+    for line in text.splitlines():
+        if pending is not None:
+            out.append(pending)
+            pending = None
+            continue
+        out.append(line)
+        if "n-timing-iterations" in line:
+            pending = str(n_timing_iterations)
+        elif "output-filename" in line:
+            pending = filename
+    return "\n".join(out) + "\n"
+
+
+def run_all_tests(setup_dir, out_root, n_records=None, n_max=9, batch=1, device=0, log=print):
+    """setup/run-all-tests.sh on the GPU path: 1 + 1 + n_max x 4 runs.  The setup files are read from
+    setup_dir (never rewritten there; the edited text goes to a scratch copy under out_root), the
+    .dat files land in out_root/<folder-name>/ like the reference's.  Returns the written paths."""
+    setup_dir, out_root = pathlib.Path(setup_dir), pathlib.Path(out_root)
+    scratch = out_root / "setup"
+    scratch.mkdir(parents=True, exist_ok=True)
+    written = []
+
+    def one(fname, plant, mode, text):
+        f = scratch / fname
+        f.write_text(text)
+        folder = setupfile.parse_setup(text, PLANTS[plant], MODES[mode]).folder_name
+        r = run_setup(f, PLANTS[plant], MODES[mode], batch=batch, out_dir=out_root / folder, n_records=n_records,
+                      device=device)
+        log(f"{fname} -> {r['paths'][0]}: mean step {r['ns_per_step'] / 1e3:.1f} us")
+        written.append(r["paths"][0])
+
+    for fname, plant, mode in ALL_TESTS_CENT:
+        one(fname, plant, mode, (setup_dir / fname).read_text())
+    for i in range(1, n_max + 1):
+        log(f"Using {i} timing iterations.")
+        for fname, plant, mode, prefix in ALL_TESTS_DIST:
+            one(fname, plant, mode, set_setup_params((setup_dir / fname).read_text(), i, f"{prefix}{i}.dat"))
+    return written
+
+
+def read_timing_data(results_root, runs=("run1", "run2", "run3", "run4", "run5"), n_max=9):
+    """read_timing_data.m:18-62: the mean of the last value of every record (the step time in ns) per
+    file; distributed runs divided by 2 (time per sub-controller), the centralised value repeated for
+    every iteration count; then the mean over the runs.  results_root holds parallel/ and serial/,
+    each with one folder per run (or the .dat files directly: runs=("",)).
+    Returns {"parallel": {"cent", "coop", "ncoop"}, "serial": {...}}, each an array of n_max values."""
+    results_root = pathlib.Path(results_root)
+
+    def mean_ns(path, n_states):
+        vals = np.array(path.read_text().split(), dtype=np.float64)
+        return vals.reshape(-1, 1 + n_states + 9)[:, -1].mean()
+
+    res = {}
+    for folder, n_states in (("parallel", 11), ("serial", 10)):
+        cent = np.zeros((n_max, len(runs))); coop = np.zeros_like(cent); ncoop = np.zeros_like(cent)
+        for r, run in enumerate(runs):
+            d = results_root / folder / run
+            cent[:, r] = mean_ns(d / "centralized.dat", n_states)
+            for i in range(1, n_max + 1):
+                coop[i - 1, r] = mean_ns(d / f"coop{i}.dat", n_states) / 2
+                ncoop[i - 1, r] = mean_ns(d / f"ncoop{i}.dat", n_states) / 2
+        res[folder] = {"cent": cent.mean(axis=1), "coop": coop.mean(axis=1), "ncoop": ncoop.mean(axis=1)}
+    return res
 
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
-    ap.add_argument("setup_file")
+    ap.add_argument("setup_file", help="a setup file, or with --all the directory that holds the six of them")
+    ap.add_argument("--all", action="store_true", help="setup/run-all-tests.sh: 1 + 1 + 9 x 4 runs")
     ap.add_argument("--plant", choices=sorted(PLANTS))
     ap.add_argument("--mode", choices=sorted(MODES))
     ap.add_argument("--batch", type=int, default=1)
@@ -115,6 +194,14 @@ def main(argv=None):
     ap.add_argument("--records", type=int)
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
+    if a.all:
+        out = a.out or "."
+        run_all_tests(a.setup_file, out, n_records=a.records, batch=a.batch, device=a.device)
+        t = read_timing_data(out, runs=("",))
+        for folder, d in t.items():
+            for k, v in d.items():
+                print(folder, k, " ".join("%.0f" % x for x in v), "ns")
+        return
     r = run_setup(a.setup_file, PLANTS.get(a.plant) if a.plant else None, MODES.get(a.mode) if a.mode else None,
                   batch=a.batch, out_dir=a.out, n_records=a.records, device=a.device)
     print(f"wrote {len(r['paths'])} file(s), first: {r['paths'][0]}; control step {r['ns_per_step'] / 1e3:.1f} us "

@@ -67,6 +67,30 @@ def main():
         print(name, full.shape, "kept", idx.size, "mean step ns", full[:, -1].mean())
     (HERE / "setups.json").write_text(json.dumps(setups, indent=1))
     np.savez_compressed(HERE / "golden_traj.npz", **arrays)
+    timing_golden()
+
+
+def timing_golden():
+    """tests/golden/timing_golden.json: the mean of the timing column of every recorded .dat file
+    (results/{parallel,serial}/run1..5/{centralized,coop1..9,ncoop1..9}.dat) and what the reference's
+    read_timing_data.m makes of them (res.parallel.coop etc.: per-controller means over the runs)."""
+    out = {"file_mean_ns": {}, "read_timing_data": {}}
+    for folder, n_states in (("parallel", 11), ("serial", 10)):
+        names = ["centralized"] + [f"coop{i}" for i in range(1, 10)] + [f"ncoop{i}" for i in range(1, 10)]
+        per = {}
+        for run in range(1, 6):
+            for name in names:
+                full = read_dat(REF / "results" / folder / f"run{run}" / f"{name}.dat", n_states)
+                per[(run, name)] = float(full[:, -1].mean())
+                out["file_mean_ns"][f"{folder}/run{run}/{name}.dat"] = per[(run, name)]
+        # read_timing_data.m:18-62, written out independently of workflow.read_timing_data
+        cent = np.mean([per[(r, "centralized")] for r in range(1, 6)])
+        out["read_timing_data"][folder] = {
+            "cent": [float(cent)] * 9,
+            "coop": [float(np.mean([per[(r, f"coop{i}")] / 2 for r in range(1, 6)])) for i in range(1, 10)],
+            "ncoop": [float(np.mean([per[(r, f"ncoop{i}")] / 2 for r in range(1, 6)])) for i in range(1, 10)]}
+        print(folder, {k: [round(v) for v in vals[:3]] for k, vals in out["read_timing_data"][folder].items()})
+    (HERE / "timing_golden.json").write_text(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":

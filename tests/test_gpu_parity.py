@@ -831,3 +831,61 @@ def test_argument_validation_added_in_round_two(setups, pkg, gpu_lib):
     torch.cuda.synchronize()
     assert torch.isfinite(d_traj).all()
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("case", ["coop-par", "cent-ser", "ncoop-ser"])
+def test_timing_window_leaves_the_results_alone(case, setups, pkg, gpu_lib):
+    """n-timing-iterations (GetNextInputWithTiming, nerve_center.h:134-182): the sweeps from
+    n_timing_iterations on are left out of the measured time.  On the device the solve is then split
+    into timed sweeps, untimed sweeps and the finishing part; records, active sets and objectives stay
+    bit-identical to the unsplit run, and every record gets a positive time of its own."""
+    s = setups[case]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    B, T = 4, 60
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 15
+    ref = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)
+    means = {}
+    for n_t in (-1, 0, 3, s.n_iterations):
+        r = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T, n_timing_iterations=n_t)
+        assert np.array_equal(r["traj"], ref["traj"]), n_t
+        assert np.array_equal(r["active"], ref["active"]) and np.array_equal(r["objective"], ref["objective"])
+        assert r["step_ns"].shape == (T,) and (r["step_ns"] > 0).all()
+        means[n_t] = r["step_ns"][5:].mean()
+    assert all(1e3 < m < 5e6 for m in means.values()), means       # microseconds to milliseconds, not garbage
+    # the host-facing call with a window
+    nc, nc2 = pkg.from_setup(s, batch=B), pkg.from_setup(s, batch=B)
+    y0 = np.stack([ol.plant_output(s.plant, x) for x in x0])
+    nc.Initialize(x0, np.zeros(4), u_def, y0)
+    nc2.Initialize(x0, np.zeros(4), u_def, y0)
+    for k in range(6):
+        y = ref["traj"][:, k, 5 + len(x_def):]
+        u, ns = nc.GetNextInputWithTiming(y, 2)
+        assert np.array_equal(u, nc2.GetNextInput(y)) and ns > 0
+        assert np.array_equal(u, ref["traj"][:, k, 1 + len(x_def):5 + len(x_def)])
+
+
+def test_run_all_tests_workflow(setups, golden, pkg, gpu_lib, tmp_path):
+    """setup/run-all-tests.sh on the GPU path (1 + 1 + n x 4 runs with the setup files rewritten per
+    run), then read_timing_data.m's aggregation over what was written."""
+    wf = pkg.workflow
+    sdir = tmp_path / "setup"
+    sdir.mkdir()
+    for case in CASES:
+        (sdir / f"setup-{case}").write_text(pkg.setupfile.format_setup(setups[case]))
+    out = tmp_path / "results"
+    written = wf.run_all_tests(sdir, out, n_records=80, n_max=2, log=lambda *_: None)
+    names = sorted(str(p.relative_to(out)) for p in written)
+    assert names == sorted([f"{f}/{n}.dat" for f in ("parallel", "serial")
+                            for n in ("centralized", "coop1", "coop2", "ncoop1", "ncoop2")])
+    for case, fname in (("coop-par", "parallel/coop2.dat"), ("ncoop-ser", "serial/ncoop1.dat"), ("cent-ser", "serial/centralized.dat")):
+        n = 11 if setups[case].plant == 0 else 10
+        got = wf.parse_records((out / fname).read_text(), n)
+        rec = golden[f"{case}/records"][:80]
+        assert got.shape == (80, 1 + n + 9)
+        assert np.abs(got[:, 1 + n:5 + n] - rec[:, 1 + n:5 + n]).max() < 1e-5
+        assert (got[:, -1] > 0).all()
+    t = wf.read_timing_data(out, runs=("",), n_max=2)
+    for folder in ("parallel", "serial"):
+        assert all(t[folder][k].shape == (2,) and (t[folder][k] > 0).all() for k in ("cent", "coop", "ncoop"))
+    assert (sdir / "setup-coop-par").read_text() == pkg.setupfile.format_setup(setups["coop-par"])   # inputs untouched

@@ -182,3 +182,43 @@ def test_cxx_driver_built_and_reports_usage():
         subprocess.check_call(["make", "-C", str(ROOT / "compressor-mpc_b200")])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_read_timing_data_reproduces_reference_aggregation(pkg, tmp_path):
+    """read_timing_data.m:18-62 as workflow.read_timing_data: a results tree whose files carry the
+    per-file mean step times of the reference's own recorded runs (tests/golden/timing_golden.json,
+    made from results/*/run1..5 by make_golden.py) aggregates to the reference's table: mean of the
+    last column, distributed runs divided by 2, mean over the five runs."""
+    import json
+    wf = pkg.workflow
+    gold = json.loads((ROOT / "tests" / "golden" / "timing_golden.json").read_text())
+    assert len(gold["file_mean_ns"]) == 2 * 5 * 19
+    for rel, mean_ns in gold["file_mean_ns"].items():
+        folder = rel.split("/")[0]
+        n = 11 if folder == "parallel" else 10
+        m = int(round(mean_ns))
+        traj = np.zeros((3, 1 + n + 8))
+        f = tmp_path / rel
+        f.parent.mkdir(parents=True, exist_ok=True)
+        f.write_text(wf.format_records(traj, n, np.array([m - 7, m, m + 7])))
+    got = wf.read_timing_data(tmp_path)
+    for folder in ("parallel", "serial"):
+        for kind in ("cent", "coop", "ncoop"):
+            want = np.array(gold["read_timing_data"][folder][kind])
+            assert got[folder][kind].shape == (9,)
+            assert np.abs(got[folder][kind] - want).max() <= 0.5, (folder, kind)     # rounding of the written integers
+    # the reference's headline numbers (BASELINE.md): about 0.35 ms centralised, 0.36 - 0.45 ms per cooperative controller
+    assert 3.4e5 < got["parallel"]["cent"][0] < 3.6e5 and 3.6e5 < got["parallel"]["coop"][0] < 3.7e5
+
+
+def test_set_setup_params_edits_like_run_all_tests(pkg, setups):
+    """setup/run-all-tests.sh:39-47 (two gawk edits): the value lines after the n-timing-iterations
+    and output-filename keys are replaced, nothing else changes."""
+    wf, sf = pkg.workflow, pkg.setupfile
+    s = setups["ncoop-ser"]
+    text = sf.format_setup(s)
+    s2 = sf.parse_setup(wf.set_setup_params(text, 4, "ncoop4.dat"), s.plant, s.mode)
+    assert (s2.n_timing_iterations, s2.output_filename, s2.n_iterations) == (4, "ncoop4.dat", s.n_iterations)
+    assert np.array_equal(s2.uwt, s.uwt) and np.array_equal(s2.sim_offsets, s.sim_offsets)
+    assert [t[0] for t in wf.ALL_TESTS_CENT + wf.ALL_TESTS_DIST] == [
+        "setup-cent-par", "setup-cent-ser", "setup-coop-par", "setup-coop-ser", "setup-ncoop-par", "setup-ncoop-ser"]
