@@ -4,5 +4,5 @@ the C ABI in include/cmpc.h.  Load with `__graft_entry__.load_package()` (the di
 carries a hyphen) or put the repo root on sys.path and import `compressor_mpc_b200`."""
 from . import capi, scenarios, setupfile, workflow  # noqa: F401
 from .capi import CmpcError, measure_fp64_peak, plant_defaults  # noqa: F401
-from .controller import InputConstraints, NerveCenter, from_setup  # noqa: F401
+from .controller import Configuration, InputConstraints, NerveCenter, SubController, from_setup  # noqa: F401
 from .setupfile import MODE_CENT, MODE_COOP, MODE_NCOOP, PLANT_PARALLEL, PLANT_SERIAL  # noqa: F401

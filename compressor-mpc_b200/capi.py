@@ -37,15 +37,19 @@ class CmpcError(RuntimeError):
         self.code = code
 
 
+MAX_CONTROLLERS = 4
+
+
 class Config(C.Structure):
     _fields_ = [
         ("plant", C.c_int32), ("mode", C.c_int32), ("p", C.c_int32), ("m", C.c_int32),
         ("Ts", C.c_double), ("n_iterations", C.c_int32), ("batch", C.c_int32),
         ("delays", C.c_int32 * 4), ("n_disturbance_states", C.c_int32),
         ("n_controllers", C.c_int32), ("n_sub_control_inputs", C.c_int32),
-        ("n_controlled_outputs", C.c_int32 * 2),
-        ("controlled_output_indices", (C.c_int32 * 4) * 2),
-        ("control_input_indices", (C.c_int32 * 4) * 2),
+        ("n_controlled_outputs", C.c_int32 * MAX_CONTROLLERS),
+        ("controlled_output_indices", (C.c_int32 * 4) * MAX_CONTROLLERS),
+        ("control_input_indices", (C.c_int32 * 4) * MAX_CONTROLLERS),
+        ("n_sub_control_inputs_per", C.c_int32 * MAX_CONTROLLERS),
     ]
 
 

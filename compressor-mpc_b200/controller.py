@@ -29,33 +29,93 @@ class InputConstraints:
     use_rate_constraints: bool = False  # never read by the reference either (mpc_qp_solver.cc:57-64)
 
 
+@dataclasses.dataclass
+class SubController:
+    """One sub-controller of a general configuration: the template arguments of the reference's
+    DistributedController / AugmentedLinearizedSystem (n_sub_control_inputs, ControlledOutputIndices,
+    ControlInputIndices) as run-time values.  input_indices None: the own inputs are the system
+    inputs that follow those of the sub-controllers before it, the others follow in system order."""
+    n_inputs: int
+    controlled_outputs: Sequence[int]
+    input_indices: Optional[Sequence[int]] = None
+
+
+@dataclasses.dataclass
+class Configuration:
+    """Run-time form of include/{parallel,serial}_compressors_constants.h (cmpc_config)."""
+    plant: int
+    controllers: Sequence[SubController]
+    p: int = 100
+    m: int = 2
+    delays: Sequence[int] = (0, 40, 0, 40)
+    n_iterations: int = 9
+    Ts: float = 0.05
+
+    def input_permutations(self):
+        out, first = [], 0
+        for sc in self.controllers:
+            if sc.input_indices is not None:
+                out.append(list(sc.input_indices))
+            else:
+                own = list(range(first, first + sc.n_inputs))
+                out.append(own + [i for i in range(4) if i not in own])
+            first += sc.n_inputs
+        return out
+
+    def to_cfg(self, batch: int) -> "capi.Config":
+        cfg = capi.Config()
+        cfg.plant, cfg.mode, cfg.p, cfg.m, cfg.Ts = self.plant, -1, self.p, self.m, self.Ts
+        cfg.n_iterations, cfg.batch, cfg.n_disturbance_states = self.n_iterations, batch, 4
+        cfg.n_controllers = len(self.controllers)
+        cfg.n_sub_control_inputs = self.controllers[0].n_inputs
+        for i in range(4):
+            cfg.delays[i] = int(self.delays[i])
+        for c, (sc, perm) in enumerate(zip(self.controllers, self.input_permutations())):
+            cfg.n_sub_control_inputs_per[c] = sc.n_inputs
+            cfg.n_controlled_outputs[c] = len(sc.controlled_outputs)
+            for i, o in enumerate(sc.controlled_outputs):
+                cfg.controlled_output_indices[c][i] = int(o)
+            for i in range(4):
+                cfg.control_input_indices[c][i] = int(perm[i])
+        return cfg
+
+
 class NerveCenter:
     """Batched NerveCenter: one cooperative / non-cooperative / centralised MPC per scenario."""
 
     def __init__(self, plant: int, mode: int, batch: int = 1, p: int = 100, n_solver_iterations: Optional[int] = None,
-                 device: int = 0, constraints: Optional[InputConstraints] = None):
-        cfg = capi.default_config(plant, mode, batch)
-        cfg.p = p
-        if n_solver_iterations is not None:
-            cfg.n_iterations = n_solver_iterations
+                 device: int = 0, constraints: Optional[InputConstraints] = None, cfg=None):
+        if cfg is None:
+            cfg = capi.default_config(plant, mode, batch)
+            cfg.p = p
+            if n_solver_iterations is not None:
+                cfg.n_iterations = n_solver_iterations
         self.cfg = cfg
-        self.plant, self.mode, self.batch, self.p = plant, mode, batch, p
+        self.plant, self.mode, self.batch, self.p, self.m = cfg.plant, mode, batch, cfg.p, cfg.m
         self.n_controllers = cfg.n_controllers
         self.n_sub_control_inputs = cfg.n_sub_control_inputs
+        self.n_sub_inputs = [cfg.n_sub_control_inputs_per[c] or cfg.n_sub_control_inputs for c in range(cfg.n_controllers)]
         self.n_controlled_outputs = [cfg.n_controlled_outputs[c] for c in range(cfg.n_controllers)]
         self.controlled_output_indices = [list(cfg.controlled_output_indices[c])[: self.n_controlled_outputs[c]]
                                           for c in range(cfg.n_controllers)]
         self.control_input_indices = [list(cfg.control_input_indices[c]) for c in range(cfg.n_controllers)]
-        self.nv = 2 * self.n_sub_control_inputs
-        self.nvo = 2 * (4 - self.n_sub_control_inputs)
+        self.nv = cfg.m * self.n_sub_control_inputs
+        self.nvo = cfg.m * (4 - self.n_sub_control_inputs)
+        self.n_delay_states = sum(cfg.delays)
         n, nin = C.c_int(), C.c_int()
-        check(lib().cmpc_plant_dims(plant, C.byref(n), C.byref(nin)))
+        check(lib().cmpc_plant_dims(cfg.plant, C.byref(n), C.byref(nin)))
         self.n_states, self.n_inputs = n.value, nin.value
         self._h = C.c_void_p()
         check(lib().cmpc_create(C.byref(cfg), device, C.byref(self._h)))
         if constraints is not None:
             for c in range(self.n_controllers):
                 self.SetConstraints(c, constraints)
+
+    @classmethod
+    def from_configuration(cls, conf: Configuration, batch: int = 1, device: int = 0) -> "NerveCenter":
+        """A configuration outside the reference's own instantiations (other delays, move horizon,
+        output partitions, up to four sub-controllers)."""
+        return cls(conf.plant, -1, batch=batch, device=device, cfg=conf.to_cfg(batch))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -74,7 +134,7 @@ class NerveCenter:
         (tuple overload, nerve_center.h:113-116; sub-matrix selection :225-234)."""
         uwt = f64(uwt)
         for c in range(self.n_controllers):
-            idx = self.control_input_indices[c][: self.n_sub_control_inputs]
+            idx = self.control_input_indices[c][: self.n_sub_inputs[c]]
             sub = f64(uwt[np.ix_(idx, idx)])
             check(lib().cmpc_set_weights(self._h, c, ptr(sub), ptr(f64(ywts[c]))))
 
@@ -204,11 +264,13 @@ class NerveCenter:
         check(lib().cmpc_get_linearization(self._h, ctrl, ptr(A), ptr(Bd), ptr(f)))
         return A, Bd, f
 
-    def qp(self, ctrl: int):
-        B, nv, nvo = self.batch, self.nv, self.nvo
+    def qp(self, ctrl: int, cross_term: bool = True):
+        B = self.batch
+        nv = self.cfg.m * self.n_sub_inputs[ctrl]
+        nvo = self.cfg.m * (4 - self.n_sub_inputs[ctrl])
         H = np.zeros((B, nv, nv)); f = np.zeros((B, nv)); G = np.zeros((B, nv, max(nvo, 1)))
-        check(lib().cmpc_get_qp(self._h, ctrl, ptr(H), ptr(f), ptr(G)))
-        return H, f, (G if nvo else None)
+        check(lib().cmpc_get_qp(self._h, ctrl, ptr(H), ptr(f), ptr(G) if cross_term else None))
+        return H, f, (G if nvo and cross_term else None)
 
     def prediction(self, ctrl: int):
         B, rows = self.batch, self.p * self.n_controlled_outputs[ctrl]
@@ -218,7 +280,7 @@ class NerveCenter:
 
     def controller_state(self, ctrl: int):
         B, n = self.batch, self.n_states
-        x = np.zeros((B, n)); dx = np.zeros((B, n + 84)); yo = np.zeros((B, 4)); uo = np.zeros((B, 4))
+        x = np.zeros((B, n)); dx = np.zeros((B, n + 4 + self.n_delay_states)); yo = np.zeros((B, 4)); uo = np.zeros((B, 4))
         check(lib().cmpc_get_controller_state(self._h, ctrl, ptr(x), ptr(dx), ptr(yo), ptr(uo)))
         return x, dx, yo, uo
 

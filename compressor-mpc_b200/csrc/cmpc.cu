@@ -74,6 +74,14 @@ int window_ns(cmpc_handle* h, size_t i, int64_t* ns) {
   return CMPC_OK;
 }
 
+// The general path keeps its parameter block in device memory: setters rewrite it (setup time only;
+// nothing may be in flight).
+int upload_generic_params(cmpc_handle* h) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h->d_genp, &h->GP, sizeof(GenParams), cudaMemcpyHostToDevice));
+  return CMPC_OK;
+}
+
 // StepParams::obs_states_free: do the observer gains leave the plant-state estimates alone?
 void update_obs_states_free(cmpc_handle* h) {
   bool free_ = true;
@@ -159,32 +167,136 @@ int cmpc_default_config(int plant, int mode, int batch, cmpc_config* cfg) {
   return CMPC_OK;
 }
 
+// Own inputs of sub-controller c.
+static int nu_of(const cmpc_config& c, int ctrl) {
+  return c.n_sub_control_inputs_per[ctrl] > 0 ? c.n_sub_control_inputs_per[ctrl] : c.n_sub_control_inputs;
+}
+
+// The tuned kernels (step_kernel.cuh) cover the reference's own instantiations: m = 2,
+// Delays = {0,40,0,40}, one of the seven controller shapes.  Everything else runs on the general
+// path (generic_kernels.cuh).  CMPC_FORCE_GENERIC=1 sends the reference's shapes there too (tests).
+static int fast_path_shape(const cmpc_config& c) {
+  if (const char* e = getenv("CMPC_FORCE_GENERIC"))
+    if (e[0] == '1') return -1;
+  const int delays[4] = {0, kDelay, 0, kDelay};
+  if (c.m != 2 || std::memcmp(c.delays, delays, sizeof delays) != 0 || c.n_controllers > 2 || c.p < 2) return -1;
+  for (int k = 0; k < c.n_controllers; ++k) {
+    if (nu_of(c, k) != c.n_sub_control_inputs) return -1;
+    for (int i = 0; i < 4; ++i) {
+      const int v = c.control_input_indices[k][i];
+      // delays are attached to the local position (aug_lin_sys.cc:160-173): the tuned kernels need
+      // the permutation to map delayed positions onto delayed plant inputs
+      if (v < 0 || v > 3 || delays[i] != delays[v]) return -1;
+    }
+  }
+  return find_shape(c);
+}
+
+static int fill_generic_params(const cmpc_config& cfg, int N, GenParams* out) {
+  GenParams& P = *out;
+  std::memset(&P, 0, sizeof P);
+  P.plant = cfg.plant; P.p = cfg.p; P.m = cfg.m; P.n_iter = cfg.n_iterations; P.batch = cfg.batch;
+  P.n_ctrl = cfg.n_controllers; P.n = N; P.n_obs = N + kNDist; P.Ts = cfg.Ts;
+  const double Ts = cfg.Ts;
+  P.rk[0] = Ts; P.rk[1] = Ts * Ts / 2.0; P.rk[2] = Ts * Ts * Ts / 6.0; P.rk[3] = Ts * Ts * Ts * Ts / 24.0;
+  if (cfg.m < 1 || 4 * cfg.m > kGenMaxPred) return fail(CMPC_ERR_UNSUPPORTED, "move horizon m must be in [1, 4]");
+  if (cfg.p < cfg.m || cfg.p > kGenMaxP) return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon must be in [m, 256]");
+  if (cfg.n_controllers < 1 || cfg.n_controllers > kGenMaxCtrl)
+    return fail(CMPC_ERR_UNSUPPORTED, "1 to 4 sub-controllers");
+  int sum_d = 0, dmax = 1, ring = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int d = cfg.delays[i];
+    // a delay of one sample has no chain state and the reference's BComposite index arithmetic
+    // (aug_lin_sys.cc:182-199) then points at another input's state
+    if (d < 0 || d == 1 || d > kGenMaxDelay) return fail(CMPC_ERR_UNSUPPORTED, "delays must be 0 or in [2, 128] samples");
+    P.delays_sys[i] = d;
+    P.ring_off[i] = ring;
+    ring += d;
+    sum_d += d;
+    dmax = d > dmax ? d : dmax;
+  }
+  if (sum_d > 240) return fail(CMPC_ERR_UNSUPPORTED, "more than 240 delay states");
+  P.ring_total = ring > 0 ? ring : 1;
+  P.dmax = dmax;
+  P.n_total = N + kNDist + sum_d;
+  P.state_stride = (N + P.n_total + 8 + 1) & ~1;
+  int in_off = 0, pred_off = 0, yref_off = 0;
+  for (int c = 0; c < cfg.n_controllers; ++c) {
+    GenCtrl& K = P.c[c];
+    K.nu = nu_of(cfg, c);
+    K.ny = cfg.n_controlled_outputs[c];
+    if (K.nu < 1 || K.nu > 4 || K.ny < 1 || K.ny > 4) return fail(CMPC_ERR_ARG, "bad input / output count of a sub-controller");
+    K.nv = cfg.m * K.nu;
+    if (K.nv > kGenMaxNv)
+      return fail(CMPC_ERR_UNSUPPORTED, "m * n_sub_control_inputs must be at most 8 (the active-set word has 32 bits)");
+    K.no = 4 - K.nu;
+    K.nvo = cfg.m * K.no;
+    K.reduced = K.nu != 4;
+    unsigned seen = 0;
+    for (int i = 0; i < 4; ++i) {
+      const int v = cfg.control_input_indices[c][i];
+      if (v < 0 || v > 3) return fail(CMPC_ERR_ARG, "control_input_indices out of range");
+      seen |= 1u << v;
+      K.ctrl_idx[i] = v;
+      K.out_idx[i] = i < K.ny ? cfg.controlled_output_indices[c][i] : 0;
+      if (K.out_idx[i] < 0 || K.out_idx[i] > 3) return fail(CMPC_ERR_ARG, "controlled_output_indices out of range");
+      // NerveCenter adds the first moves of sub-controller c to the system inputs that follow those
+      // of the sub-controllers before it (nerve_center.h:313-319) and hands every sub-controller
+      // du[ControlInputIndices] (:322-328): the two agree only for this layout
+      if (i < K.nu && K.reduced && v != in_off + i)
+        return fail(CMPC_ERR_ARG, "the own inputs of a sub-controller must be the system inputs that follow "
+                                  "those of the sub-controllers before it (nerve_center.h:313-328)");
+    }
+    if (seen != 0xF) return fail(CMPC_ERR_ARG, "control_input_indices must be a permutation");
+    // each sub-controller's AugmentedLinearizedSystem sees the delays in its own input order; a
+    // controller that is not reduced keeps the system order (aug_lin_sys.cc:158)
+    int n_del = 0;
+    for (int i = 0; i < 4; ++i) {
+      K.delay[i] = cfg.delays[K.reduced ? K.ctrl_idx[i] : i];
+      if (K.delay[i] > 0) ++n_del;
+    }
+    int head = N + kNDist, chain = N + kNDist + n_del;
+    for (int i = 0; i < 4; ++i) {
+      K.head[i] = K.chain[i] = -1;
+      if (K.delay[i] > 0) {
+        K.head[i] = head++;
+        K.chain[i] = chain;
+        chain += K.delay[i] - 1;
+      }
+    }
+    K.pred_off = pred_off; K.in_off = in_off; K.yref_off = yref_off;
+    pred_off += K.nv; in_off += K.nu; yref_off += cfg.p * K.ny;
+    for (int i = 0; i < 4; ++i) { K.lower[i] = -1e30; K.upper[i] = 1e30; K.rate_lower[i] = -1e30; K.rate_upper[i] = 1e30; }
+    for (int i = 0; i < K.ny; ++i) K.Q[i * K.ny + i] = 1.0;
+    for (int i = 0; i < K.nu; ++i) K.R[i * K.nu + i] = 1.0;
+    for (int i = 0; i < 4; ++i) K.M[(N + i) * 4 + i] = 1.0;   // default gain [0; I]
+  }
+  if (in_off != 4) return fail(CMPC_ERR_ARG, "the sub-controllers' own inputs must add up to the four control inputs");
+  P.n_pred = pred_off;
+  return CMPC_OK;
+}
+
 int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   if (!cfg || !out) return fail(CMPC_ERR_ARG, "null argument");
   *out = nullptr;
   if (cfg->batch <= 0) return fail(CMPC_ERR_ARG, "batch must be positive");
-  if (cfg->m != 2) return fail(CMPC_ERR_UNSUPPORTED, "only move horizon m = 2 is built");
-  if (cfg->p < 2 || cfg->p > 256) return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon must be in [2, 256]");
-  const int delays[4] = {0, kDelay, 0, kDelay};
-  if (std::memcmp(cfg->delays, delays, sizeof delays) != 0 || cfg->n_disturbance_states != kNDist)
-    return fail(CMPC_ERR_UNSUPPORTED, "only Delays = {0,40,0,40} with 4 disturbance states is built");
+  if (cfg->plant != 0 && cfg->plant != 1) return fail(CMPC_ERR_ARG, "plant must be 0 or 1");
   if (cfg->n_iterations < 1) return fail(CMPC_ERR_ARG, "n_iterations must be >= 1");
-  const int shape = find_shape(*cfg);
-  if (shape < 0) return fail(CMPC_ERR_UNSUPPORTED, "no kernel instantiated for this controller shape");
-  for (int c = 0; c < cfg->n_controllers; ++c) {
-    unsigned seen = 0;
-    for (int i = 0; i < 4; ++i) {
-      const int v = cfg->control_input_indices[c][i];
-      if (v < 0 || v > 3) return fail(CMPC_ERR_ARG, "control_input_indices out of range");
-      seen |= 1u << v;
-      // delays are attached to the local position (aug_lin_sys.cc:160-173); the permutation
-      // must map delayed positions onto delayed plant inputs
-      if (delays[i] != delays[v]) return fail(CMPC_ERR_UNSUPPORTED, "permutation mixes delayed and undelayed inputs");
-    }
-    if (seen != 0xF) return fail(CMPC_ERR_ARG, "control_input_indices must be a permutation");
-    for (int i = 0; i < cfg->n_controlled_outputs[c]; ++i)
+  if (cfg->n_disturbance_states != kNDist)
+    return fail(CMPC_ERR_UNSUPPORTED, "4 disturbance states (one per plant output, as in both plants of the reference)");
+  if (cfg->n_controllers < 1 || cfg->n_controllers > CMPC_MAX_CONTROLLERS) return fail(CMPC_ERR_ARG, "bad n_controllers");
+  for (int c = 0; c < cfg->n_controllers; ++c)
+    for (int i = 0; i < 4 && i < cfg->n_controlled_outputs[c]; ++i)
       if (cfg->controlled_output_indices[c][i] < 0 || cfg->controlled_output_indices[c][i] > 3)
         return fail(CMPC_ERR_ARG, "controlled_output_indices out of range");
+  const int shape = fast_path_shape(*cfg);
+  int N = 0, NIN = 0;
+  cmpc_plant_dims(cfg->plant, &N, &NIN);
+  GenParams gp;
+  if (shape < 0) {
+    if (int rc = fill_generic_params(*cfg, N, &gp)) return rc;
+  } else if (cfg->p > 256) {
+    return fail(CMPC_ERR_UNSUPPORTED, "prediction horizon must be in [2, 256]");
   }
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
@@ -196,12 +308,17 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->shape = shape;
-  cmpc_plant_dims(cfg->plant, &h->N, &h->NIN);
+  h->generic = shape < 0;
+  h->ops = h->generic ? (cfg->plant == 0 ? &kOps_generic_par : &kOps_generic_ser) : kShapeOps[shape];
+  h->N = N;
+  h->NIN = NIN;
   h->NCTRL = cfg->n_controllers;
-  h->NV = 2 * cfg->n_sub_control_inputs;
-  h->NVO = 2 * (4 - cfg->n_sub_control_inputs);
+  h->NV = cfg->m * cfg->n_sub_control_inputs;
+  h->NVO = cfg->m * (4 - cfg->n_sub_control_inputs);
   std::memset(&h->P, 0, sizeof h->P);
   std::memset(&h->G, 0, sizeof h->G);
+  std::memset(&h->GS, 0, sizeof h->GS);
+  h->GP = gp;
   StepParams& P = h->P;
   P.p = cfg->p;
   P.b_max = (cfg->p + kBaby - 1) / kBaby;
@@ -215,8 +332,8 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
     const double Ts = cfg->Ts;
     P.rk[0] = Ts; P.rk[1] = Ts * Ts / 2.0; P.rk[2] = Ts * Ts * Ts / 6.0; P.rk[3] = Ts * Ts * Ts * Ts / 24.0;
   }
-  const int B = cfg->batch, NC = h->NCTRL, N = h->N;
-  for (int c = 0; c < NC; ++c) {
+  const int B = cfg->batch, NC = h->NCTRL;
+  for (int c = 0; c < NC && c < 2 && !h->generic; ++c) {
     CtrlParams& cp = P.c[c];
     const int ny = cfg->n_controlled_outputs[c], nu = cfg->n_sub_control_inputs;
     for (int i = 0; i < 4; ++i) {
@@ -228,23 +345,43 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
     for (int i = 0; i < nu; ++i) cp.R[i * nu + i] = 1.0;
     for (int i = 0; i < 4; ++i) cp.M[(N + i) * 4 + i] = 1.0;  // default gain [0; I]
   }
-  update_obs_states_free(h);
+  if (!h->generic) update_obs_states_free(h);
   DeviceState& G = h->G;
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  A(dalloc(&G.ctrl, size_t(B) * NC * kCtrlStateStride));
-  A(dalloc(&G.guess, size_t(B) * NC));
-  A(dalloc(&G.scen, size_t(B) * kScenStateStride));
-  A(dalloc(&G.u_offset, size_t(B) * h->NIN));
-  A(dalloc(&G.work, size_t(B) * NC * kWorkStride));
-  A(dalloc(&G.qpH, size_t(B) * NC * h->NV * h->NV));
-  A(dalloc(&G.qpf, size_t(B) * NC * h->NV));
-  A(dalloc(&G.qpG, size_t(B) * NC * h->NV * (h->NVO > 0 ? h->NVO : 1)));
-  A(dalloc(&G.status, size_t(B) * NC));
-  A(dalloc(&G.active, size_t(B) * NC));
-  A(dalloc(&G.objective, size_t(B) * NC));
-  A(dalloc(&G.ticks, size_t(B) * 16));
-  A(dalloc(&h->d_yref, size_t(NC) * cfg->p * 4));
+  if (h->generic) {
+    GenState& S = h->GS;
+    A(dalloc(&S.ctrl, size_t(B) * NC * gp.state_stride));
+    A(dalloc(&S.guess, size_t(B) * NC));
+    A(dalloc(&S.scen, size_t(B) * kGenScenStride));
+    A(dalloc(&S.u_offset, size_t(B) * NIN));
+    A(dalloc(&S.qpH, size_t(B) * NC * 64));
+    A(dalloc(&S.qpf, size_t(B) * NC * 8));
+    A(dalloc(&S.status, size_t(B) * NC));
+    A(dalloc(&S.active, size_t(B) * NC));
+    A(dalloc(&S.objective, size_t(B) * NC));
+    A(dalloc(&h->d_yref, size_t(NC) * cfg->p * 4));
+    A(dalloc(&h->d_genp, 1));
+    A(dalloc(&h->d_ring, size_t(B) * gp.ring_total));
+    S.yref = h->d_yref;
+    // the read-back entry points find results where the tuned path keeps them
+    G.status = S.status; G.active = S.active; G.objective = S.objective;
+  } else {
+    A(dalloc(&G.ctrl, size_t(B) * NC * kCtrlStateStride));
+    A(dalloc(&G.guess, size_t(B) * NC));
+    A(dalloc(&G.scen, size_t(B) * kScenStateStride));
+    A(dalloc(&G.u_offset, size_t(B) * h->NIN));
+    A(dalloc(&G.work, size_t(B) * NC * kWorkStride));
+    A(dalloc(&G.qpH, size_t(B) * NC * h->NV * h->NV));
+    A(dalloc(&G.qpf, size_t(B) * NC * h->NV));
+    A(dalloc(&G.qpG, size_t(B) * NC * h->NV * (h->NVO > 0 ? h->NVO : 1)));
+    A(dalloc(&G.status, size_t(B) * NC));
+    A(dalloc(&G.active, size_t(B) * NC));
+    A(dalloc(&G.objective, size_t(B) * NC));
+    A(dalloc(&G.ticks, size_t(B) * 16));
+    A(dalloc(&h->d_yref, size_t(NC) * cfg->p * 4));
+    A(dalloc(&h->d_ring, size_t(B) * 2 * kDelay));
+  }
   A(dalloc(&h->d_y, size_t(B) * 4));
   A(dalloc(&h->d_u, size_t(B) * 4));
   A(dalloc(&h->d_xinit, size_t(B) * N));
@@ -252,14 +389,14 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
   A(dalloc(&h->d_uinitfull, size_t(B) * h->NIN));
   A(dalloc(&h->d_yinit, size_t(B) * 4));
   A(dalloc(&h->d_x, size_t(B) * N));
-  A(dalloc(&h->d_ring, size_t(B) * 2 * kDelay));
   A(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (e == cudaSuccess && h->generic) e = cudaMemcpy(h->d_genp, &h->GP, sizeof(GenParams), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cmpc_destroy(h);
     return fail(CMPC_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   }
   P.yref = h->d_yref;
-  int rc = kShapeOps[shape]->setup(h);
+  int rc = h->ops->setup(h);
   if (rc) {
     cmpc_destroy(h);
     return rc;
@@ -273,7 +410,10 @@ int cmpc_destroy(cmpc_handle* h) {
   DeviceGuard device_guard_(h->device);
   cudaDeviceSynchronize();
   DeviceState& G = h->G;
-  void* ptrs[] = {G.ctrl, G.guess, G.scen, G.u_offset, G.work, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
+  if (h->generic) G.status = nullptr, G.active = nullptr, G.objective = nullptr;   // aliases of the GenState arrays
+  GenState& S = h->GS;
+  void* ptrs[] = {S.ctrl, S.guess, S.scen, S.u_offset, S.qpH, S.qpf, S.status, S.active, S.objective, h->d_genp,
+                  G.ctrl, G.guess, G.scen, G.u_offset, G.work, G.qpH, G.qpf, G.qpG, G.lin, G.etab, G.status,
                   G.active, G.objective, G.ticks, h->d_yref, h->d_y, h->d_u, h->d_xinit, h->d_uinit,
                   h->d_uinitfull, h->d_yinit, h->d_x, h->d_ring, h->d_block_end, h->d_block_off,
                   h->d_step_end, h->d_step_off, h->d_rec};
@@ -289,8 +429,7 @@ int cmpc_destroy(cmpc_handle* h) {
 int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* ywt) {
   CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
-  CtrlParams& cp = h->P.c[ctrl];
-  const int ny = h->cfg.n_controlled_outputs[ctrl], nu = h->cfg.n_sub_control_inputs;
+  const int ny = h->cfg.n_controlled_outputs[ctrl], nu = nu_of(h->cfg, ctrl);
   if (ywt)
     for (int i = 0; i < ny; ++i)
       for (int j = 0; j < i; ++j)
@@ -307,6 +446,13 @@ int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* 
     if (!std::isfinite(uwt[i])) return fail(CMPC_ERR_ARG, "uwt must be finite");
   for (int i = 0; ywt && i < ny * ny; ++i)
     if (!std::isfinite(ywt[i])) return fail(CMPC_ERR_ARG, "ywt must be finite");
+  if (h->generic) {
+    GenCtrl& K = h->GP.c[ctrl];
+    if (uwt) std::memcpy(K.R, uwt, sizeof(double) * nu * nu);
+    if (ywt) std::memcpy(K.Q, ywt, sizeof(double) * ny * ny);
+    return upload_generic_params(h);
+  }
+  CtrlParams& cp = h->P.c[ctrl];
   if (uwt) std::memcpy(cp.R, uwt, sizeof(double) * nu * nu);
   if (ywt) std::memcpy(cp.Q, ywt, sizeof(double) * ny * ny);
   return CMPC_OK;
@@ -322,14 +468,24 @@ int cmpc_set_output_reference(cmpc_handle* h, const double* yref) {
     const int ny = h->cfg.n_controlled_outputs[c];
     for (int r = 0; r < p; ++r)
       for (int i = 0; i < ny; ++i)
-        sub[(size_t(c) * p + r) * ny + i] = yref[r * 4 + h->cfg.controlled_output_indices[c][i]];
+        sub[size_t(c) * p * 4 + size_t(r) * ny + i] = yref[r * 4 + h->cfg.controlled_output_indices[c][i]];
+  }
+  if (h->generic) {   // one p x n_y block per sub-controller, back to back (GenCtrl::yref_off)
+    std::vector<double> packed;
+    for (int c = 0; c < h->NCTRL; ++c) {
+      const int nyc = h->cfg.n_controlled_outputs[c];
+      packed.insert(packed.end(), sub.begin() + size_t(c) * p * 4, sub.begin() + size_t(c) * p * 4 + size_t(p) * nyc);
+    }
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->d_yref, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return CMPC_OK;
   }
   // device layout [NCTRL][p][NY] with NY common to both controllers
   const int ny = h->cfg.n_controlled_outputs[0];
   std::vector<double> packed(size_t(h->NCTRL) * p * ny);
   for (int c = 0; c < h->NCTRL; ++c)
     for (int r = 0; r < p; ++r)
-      for (int i = 0; i < ny; ++i) packed[(size_t(c) * p + r) * ny + i] = sub[(size_t(c) * p + r) * ny + i];
+      for (int i = 0; i < ny; ++i) packed[(size_t(c) * p + r) * ny + i] = sub[size_t(c) * p * 4 + size_t(r) * ny + i];
   CU(cudaMemcpy(h->d_yref, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice));
   return CMPC_OK;
 }
@@ -339,17 +495,24 @@ int cmpc_set_constraints(cmpc_handle* h, int ctrl, const double* lower, const do
   CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   if (!lower || !upper || !rate_lower || !rate_upper) return fail(CMPC_ERR_ARG, "null constraint array");
-  CtrlParams& cp = h->P.c[ctrl];
-  // a bound is a finite number or +-infinity (kept as +-1e30, which no input ever reaches);
-  // NaN and an empty interval are refused here instead of surfacing as failed QPs at every step
+  const int nu = nu_of(h->cfg, ctrl);
+  // a bound is a finite number or +-infinity (kept as +-1e30, which no input ever reaches); NaN is
+  // refused.  lower > upper is accepted like the reference accepts it: every QP is then infeasible
+  // and every step applies the zero move (mpc_qp_solver.cc:66-69), with status != 0 in cmpc_get_step_info.
   auto clamp = [](double v) { return v > 1e30 ? 1e30 : (v < -1e30 ? -1e30 : v); };
-  for (int i = 0; i < h->cfg.n_sub_control_inputs; ++i) {
+  for (int i = 0; i < nu; ++i)
     if (std::isnan(lower[i]) || std::isnan(upper[i]) || std::isnan(rate_lower[i]) || std::isnan(rate_upper[i]))
       return fail(CMPC_ERR_ARG, "constraint bounds must not be NaN");
-    if (lower[i] > upper[i] || rate_lower[i] > rate_upper[i])
-      return fail(CMPC_ERR_ARG, "constraint lower bound above upper bound");
+  if (h->generic) {
+    GenCtrl& K = h->GP.c[ctrl];
+    for (int i = 0; i < nu; ++i) {
+      K.lower[i] = clamp(lower[i]); K.upper[i] = clamp(upper[i]);
+      K.rate_lower[i] = clamp(rate_lower[i]); K.rate_upper[i] = clamp(rate_upper[i]);
+    }
+    return upload_generic_params(h);
   }
-  for (int i = 0; i < h->cfg.n_sub_control_inputs; ++i) {
+  CtrlParams& cp = h->P.c[ctrl];
+  for (int i = 0; i < nu; ++i) {
     cp.lower[i] = clamp(lower[i]); cp.upper[i] = clamp(upper[i]);
     cp.rate_lower[i] = clamp(rate_lower[i]); cp.rate_upper[i] = clamp(rate_upper[i]);
   }
@@ -359,6 +522,10 @@ int cmpc_set_constraints(cmpc_handle* h, int ctrl, const double* lower, const do
 int cmpc_set_observer_gain(cmpc_handle* h, int ctrl, const double* M) {
   CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL || !M) return fail(CMPC_ERR_ARG, "bad argument");
+  if (h->generic) {
+    std::memcpy(h->GP.c[ctrl].M, M, sizeof(double) * (h->N + kNDist) * 4);
+    return upload_generic_params(h);
+  }
   std::memcpy(h->P.c[ctrl].M, M, sizeof(double) * (h->N + kNDist) * 4);
   update_obs_states_free(h);
   return CMPC_OK;
@@ -366,6 +533,8 @@ int cmpc_set_observer_gain(cmpc_handle* h, int ctrl, const double* M) {
 
 int cmpc_set_capture(cmpc_handle* h, int on) {
   CMPC_ENTER(h);
+  if (h->generic && on)
+    return fail(CMPC_ERR_UNSUPPORTED, "the linearisation / prediction read-back hooks exist on the tuned path only");
   const size_t B = h->cfg.batch, NC = h->NCTRL;
   const size_t ny = h->cfg.n_controlled_outputs[0];
   if (on && !h->G.lin) {
@@ -390,7 +559,7 @@ int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
   CU(cudaMemcpy(h->d_uinit, u_init, B * 4 * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_uinitfull, u_init_full, B * h->NIN * sizeof(double), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_yinit, y_init, B * 4 * sizeof(double), cudaMemcpyHostToDevice));
-  int rc = kShapeOps[h->shape]->init(h, h->d_xinit, h->d_uinit, h->d_uinitfull, h->d_yinit, h->stream);
+  int rc = h->ops->init(h, h->d_xinit, h->d_uinit, h->d_uinitfull, h->d_yinit, h->stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
   h->initialized = true;
@@ -403,7 +572,7 @@ int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_de
   if (!h->initialized) return fail(CMPC_ERR_STATE, "cmpc_initialize has not been called");
   if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
   if (!y_dev || !u_dev) return fail(CMPC_ERR_ARG, "null argument");
-  return kShapeOps[h->shape]->step(h, y_dev, u_dev, static_cast<cudaStream_t>(stream));
+  return h->ops->step(h, y_dev, u_dev, static_cast<cudaStream_t>(stream));
 }
 
 int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
@@ -413,7 +582,7 @@ int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
   if (!y || !u) return fail(CMPC_ERR_ARG, "null argument");
   const size_t bytes = size_t(h->cfg.batch) * 4 * sizeof(double);
   CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, h->stream));
-  int rc = kShapeOps[h->shape]->step(h, h->d_y, h->d_u, h->stream);
+  int rc = h->ops->step(h, h->d_y, h->d_u, h->stream);
   if (rc) return rc;
   CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -433,7 +602,7 @@ int cmpc_get_next_input_timed(cmpc_handle* h, const double* y, double* u, int n_
   CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, h->stream));
   h->window_on = true;
   h->window_n = n_timing_iterations;
-  int rc = kShapeOps[h->shape]->step(h, h->d_y, h->d_u, h->stream);
+  int rc = h->ops->step(h, h->d_y, h->d_u, h->stream);
   h->window_on = false;
   if (rc) return rc;
   CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -492,7 +661,7 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
   A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;
   A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
   A.qp_status = qp_status_dev; A.n_steps = total_steps; A.rec_base = 0;
-  const int rc = kShapeOps[h->shape]->closed_loop(h, first_step, n_steps, x0_dev, A, reinit,
+  const int rc = h->ops->closed_loop(h, first_step, n_steps, x0_dev, A, reinit,
                                                    static_cast<cudaStream_t>(stream));
   h->stream_next = -1;   // a cmpc_closed_loop_start / _step sequence does not survive a run of this kind
   if (rc == CMPC_OK) {
@@ -540,7 +709,7 @@ int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* re
   A.block_end = h->d_step_end; A.block_off = h->d_step_off; A.n_blocks = 1;
   A.traj = h->d_rec; A.qp_active = nullptr; A.qp_objective = nullptr; A.qp_status = nullptr;
   A.n_steps = 1; A.rec_base = k;
-  if (int rc = kShapeOps[h->shape]->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) {
+  if (int rc = h->ops->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) {
     h->stream_next = -1;
     h->loop_started = false;
     return rc;
@@ -666,6 +835,16 @@ int cmpc_get_linearization(cmpc_handle* h, int ctrl, double* Aorig, double* Bd, 
 int cmpc_get_qp(cmpc_handle* h, int ctrl, double* H, double* f, double* Gx) {
   CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
+  if (h->generic) {   // H nv x nv and f nv of this sub-controller; the cross term is not kept in HBM
+    if (Gx) return fail(CMPC_ERR_UNSUPPORTED, "the cross term is read back on the tuned path only");
+    const size_t B = h->cfg.batch, NC = h->NCTRL, nv = h->GP.c[ctrl].nv;
+    CU(cudaDeviceSynchronize());
+    if (H) CU(cudaMemcpy2D(H, nv * nv * sizeof(double), h->GS.qpH + ctrl * 64, NC * 64 * sizeof(double),
+                           nv * nv * sizeof(double), B, cudaMemcpyDeviceToHost));
+    if (f) CU(cudaMemcpy2D(f, nv * sizeof(double), h->GS.qpf + ctrl * 8, NC * 8 * sizeof(double), nv * sizeof(double), B,
+                           cudaMemcpyDeviceToHost));
+    return CMPC_OK;
+  }
   const size_t B = h->cfg.batch, NC = h->NCTRL, NV = h->NV, NVO = h->NVO;
   CU(cudaDeviceSynchronize());
   if (H) CU(cudaMemcpy2D(H, NV * NV * sizeof(double), h->G.qpH + ctrl * NV * NV, NC * NV * NV * sizeof(double),
@@ -718,6 +897,20 @@ int cmpc_get_controller_state(cmpc_handle* h, int ctrl, double* x_hat, double* d
   CMPC_ENTER(h);
   if (ctrl < 0 || ctrl >= h->NCTRL) return fail(CMPC_ERR_ARG, "bad controller index");
   const size_t B = h->cfg.batch;
+  if (h->generic) {   // x_hat[n] | dx_aug[n_total] (the reference's state order) | y_old[4] | u_old[4]
+    const size_t st = h->GP.state_stride, nt = h->GP.n_total, n = h->N;
+    std::vector<double> buf(B * h->NCTRL * st);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(buf.data(), h->GS.ctrl, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b) {
+      const double* r = buf.data() + (b * h->NCTRL + ctrl) * st;
+      if (x_hat) std::memcpy(x_hat + b * n, r, sizeof(double) * n);
+      if (dx_aug) std::memcpy(dx_aug + b * nt, r + n, sizeof(double) * nt);
+      if (y_old) std::memcpy(y_old + b * 4, r + n + nt, sizeof(double) * 4);
+      if (u_old) std::memcpy(u_old + b * 4, r + n + nt + 4, sizeof(double) * 4);
+    }
+    return CMPC_OK;
+  }
   std::vector<double> buf(B * h->NCTRL * kCtrlStateStride);
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(buf.data(), h->G.ctrl, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));

@@ -8,8 +8,13 @@
 #include <vector>
 
 #include "cmpc.h"
+#include "generic_params.cuh"
 #include "plant_kernels.cuh"
 #include "step_kernel.cuh"
+
+namespace cmpc {
+struct ShapeOps;
+}
 
 namespace cmpc {
 
@@ -77,6 +82,12 @@ struct cmpc_handle {
   int N = 0, NIN = 0, NV = 0, NVO = 0, NCTRL = 0;
   cmpc::StepParams P;
   cmpc::DeviceState G;
+  // general configuration path (generic_kernels.cuh): its parameter block lives in device memory
+  bool generic = false;
+  cmpc::GenParams GP;
+  cmpc::GenState GS;
+  cmpc::GenParams* d_genp = nullptr;
+  const cmpc::ShapeOps* ops = nullptr;   // launch functions of this handle's path
   double* d_yref = nullptr;
   double *d_y = nullptr, *d_u = nullptr;  // [B][4]
   double *d_xinit = nullptr, *d_uinit = nullptr, *d_uinitfull = nullptr, *d_yinit = nullptr;
@@ -125,5 +136,6 @@ struct ShapeOps {
 };
 constexpr int kNumShapes = 7;
 extern const ShapeOps* const kShapeOps[kNumShapes];
+extern const ShapeOps kOps_generic_par, kOps_generic_ser;
 
 }  // namespace cmpc

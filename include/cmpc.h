@@ -34,28 +34,43 @@ enum { CMPC_MODE_CENTRALIZED = 0, CMPC_MODE_COOPERATIVE = 1, CMPC_MODE_NONCOOPER
 
 #define CMPC_N_CONTROL_INPUTS 4   /* plant inputs {0,3,4,7}: torque1, recycle1, torque2, recycle2 */
 #define CMPC_N_OUTPUTS 4
-#define CMPC_MAX_CONTROLLERS 2
+#define CMPC_MAX_CONTROLLERS 4   /* NerveCenter takes a parameter pack of sub-controllers (nerve_center.h:19-38) */
 
 typedef struct cmpc_handle cmpc_handle;
 
 /* Runtime form of the reference's compile-time configuration
- * (include/parallel_compressors_constants.h:70-93, include/serial_compressors_constants.h:84-109,
- *  include/common-variables.h:20-112). */
+ * (include/constexpr_array.h:10-142, include/parallel_compressors_constants.h:70-93,
+ *  include/serial_compressors_constants.h:84-109, include/common-variables.h:20-112,
+ *  the sub-controller pack of include/nerve_center.h:19-38).
+ * The reference's own instantiations (m = 2, Delays = {0,40,0,40}, its seven controller shapes) run
+ * on kernels tuned for them; every other configuration runs on a general path with the same
+ * results contract:
+ *   delays     per control input {torque1, recycle1, torque2, recycle2}: 0 or 2..128 samples; every
+ *              sub-controller's AugmentedLinearizedSystem sees them in its own input order
+ *   m          1..4 with m * (own inputs) <= 8 per sub-controller;  p in [m, 256]
+ *   partitions 1..4 sub-controllers, each with its own input count (n_sub_control_inputs_per, summing
+ *              to 4; the own inputs of sub-controller c are the system inputs that follow those of
+ *              the sub-controllers before it, as NerveCenter assumes, nerve_center.h:313-328) and its
+ *              own controlled outputs (1..4 of the plant's 4)
+ * With more than two sub-controllers the plans of the others reach a sub-controller exactly as in
+ * the reference: concatenated in controller order and paired with the columns of Su_other by
+ * position (nerve_center.h:281-286, distributed_solver.h:109-115). */
 typedef struct cmpc_config {
   int32_t plant;                 /* CMPC_PLANT_* */
-  int32_t mode;                  /* CMPC_MODE_* */
+  int32_t mode;                  /* CMPC_MODE_* (only read by cmpc_default_config) */
   int32_t p;                     /* prediction horizon (reference: 100; sweep: 200) */
-  int32_t m;                     /* move horizon (2) */
+  int32_t m;                     /* move horizon (reference: 2) */
   double Ts;                     /* sampling time (0.05 s) */
   int32_t n_iterations;          /* solver sweeps per step: setup key n-iterations (1 cent, 9 distributed) */
   int32_t batch;                 /* B independent scenarios */
-  int32_t delays[4];             /* Delays = {0,40,0,40} */
+  int32_t delays[4];             /* Delays (reference: {0,40,0,40}), per control input in plant order */
   int32_t n_disturbance_states;  /* 4 */
-  int32_t n_controllers;         /* 1 or 2 */
+  int32_t n_controllers;         /* 1..CMPC_MAX_CONTROLLERS */
   int32_t n_sub_control_inputs;  /* own inputs per sub-controller: 4 (cent) or 2 */
   int32_t n_controlled_outputs[CMPC_MAX_CONTROLLERS];
   int32_t controlled_output_indices[CMPC_MAX_CONTROLLERS][4]; /* ControlledOutputIndices */
-  int32_t control_input_indices[CMPC_MAX_CONTROLLERS][4];     /* ControlInputIndices{1,2} */
+  int32_t control_input_indices[CMPC_MAX_CONTROLLERS][4];     /* ControlInputIndices: own inputs first */
+  int32_t n_sub_control_inputs_per[CMPC_MAX_CONTROLLERS];     /* own inputs of each sub-controller; 0 = n_sub_control_inputs */
 } cmpc_config;
 
 /* Fill cfg with the reference's constants for one of its six workflows. */
@@ -74,11 +89,15 @@ int cmpc_destroy(cmpc_handle* h);
 const char* cmpc_last_error(void);
 
 /* NerveCenter::SetWeights, tuple overload (nerve_center.h:113-116 -> mpc_qp_solver.h:62-80).
- * uwt: n_sub_control_inputs^2 (this controller's sub-matrix), ywt: n_controlled_outputs^2. */
+ * uwt: n_u x n_u (this controller's sub-matrix of the full input weight, n_u its own inputs),
+ * ywt: n_controlled_outputs^2.  Both must be symmetric (CMPC_ERR_UNSUPPORTED otherwise: H is kept
+ * as a symmetric matrix) and finite. */
 int cmpc_set_weights(cmpc_handle* h, int ctrl, const double* uwt, const double* ywt);
 /* NerveCenter::SetOutputReference (nerve_center.h:119-122): yref is p x 4 (all plant outputs). */
 int cmpc_set_output_reference(cmpc_handle* h, const double* yref);
-/* InputConstraints (include/input_constraints.h:11-27), n_sub_control_inputs entries each. */
+/* InputConstraints (include/input_constraints.h:11-27), one entry per own input each.  +-infinity
+ * means unbounded; NaN is CMPC_ERR_ARG.  lower > upper is taken as it is, like the reference does:
+ * every QP is infeasible and every step applies the zero move (mpc_qp_solver.cc:66-69). */
 int cmpc_set_constraints(cmpc_handle* h, int ctrl, const double* lower, const double* upper,
                          const double* rate_lower, const double* rate_upper);
 /* Observer ctor's ObserverMatrix M, (n_states+n_dist) x 4 row-major (observer.h:31-33).
@@ -107,7 +126,15 @@ int cmpc_get_next_input_timed(cmpc_handle* h, const double* y, double* u, int n_
 /* Same with device-resident y/u (B x 4 doubles each) on `stream` (a cudaStream_t), no sync. */
 int cmpc_get_next_input_device(cmpc_handle* h, const double* y_dev, double* u_dev, void* stream);
 
-/* Per-scenario result of the last step's final solver sweep (mpc_qp_solver.cc:62-75):
+/* Deviation from the reference at the QP solver, by design: the reference hands every QP to qpOASES
+ * with a working-set-recalculation budget of 10 (n_wsr_max, mpc_qp_solver.h:24, mpc_qp_solver.cc:50-69)
+ * and applies a zero move when qpOASES needs more.  The solver here has no such budget: it returns the
+ * exact minimiser whenever the QP is feasible and H is positive definite, and the zero move only when
+ * it is not (status != 0).  Steps on which the reference would have run out of its budget therefore
+ * differ; none of the reference's six recorded runs contains one (they are reproduced over all
+ * 10 000 records), and the budget depends on qpOASES's homotopy path, which is not restated.
+ *
+ * Per-scenario result of the last step's final solver sweep (mpc_qp_solver.cc:62-75):
  * status B x n_ctrl (0 ok; !=0 => that controller applied zeros), active B x n_ctrl
  * (bitmask over 4*nv one-sided constraints: [0,nv) z>=lb, [nv,2nv) z<=ub, [2nv,3nv) rate>=,
  * [3nv,4nv) rate<=), objective B x n_ctrl (1/2 z'Hz + f'z).  Any pointer may be NULL. */

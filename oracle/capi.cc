@@ -17,9 +17,9 @@ namespace {
 struct Setup {
   SystemConfig sc;
   double uwt[16];
-  double ywt[2][16];
-  InputConstraints ic[2];
-  std::vector<double> M[2];
+  double ywt[kMaxControllers][16];
+  InputConstraints ic[kMaxControllers];
+  std::vector<double> M[kMaxControllers];
   std::vector<double> yref;  // p × 4
 };
 
@@ -71,7 +71,7 @@ void DefaultConfig(int plant, int mode, SystemConfig* sc) {
 
 NerveCenter* MakeNerveCenter(const Setup& s) {
   NerveCenter* nc = new NerveCenter(s.sc);
-  const double* ywts[2] = {s.ywt[0], s.ywt[1]};
+  const double* ywts[kMaxControllers] = {s.ywt[0], s.ywt[1], s.ywt[2], s.ywt[3]};
   nc->SetWeights(s.uwt, ywts);
   nc->SetOutputReference(s.yref.data());
   for (int c = 0; c < s.sc.n_controllers; ++c) {
@@ -85,17 +85,54 @@ NerveCenter* MakeNerveCenter(const Setup& s) {
 
 extern "C" {
 
+static void* FinishCreate(Handle* h);
+
 void* orc_create(int plant, int mode, int p, int n_iter) {
   Handle* h = new Handle;
   DefaultConfig(plant, mode, &h->s.sc);
   if (p > 0) h->s.sc.p = p;
   if (n_iter > 0) h->s.sc.n_solver_iterations = n_iter;
+  return FinishCreate(h);
+}
+
+// Runtime form of the reference's template configuration (constexpr_array.h,
+// {parallel,serial}_compressors_constants.h, nerve_center.h:19-38): any prediction / move
+// horizon, per-input delays (system order; each sub-controller's AugmentedLinearizedSystem gets
+// them in its own input order), up to four sub-controllers with their own input counts, output
+// partitions and input permutations.
+void* orc_create_config(int plant, int p, int m, int n_iter, const int* delays, int n_controllers,
+                        const int* n_sub_control_inputs, const int* n_controlled_outputs,
+                        const int* controlled_output_indices /* n_ctrl x 4 */,
+                        const int* control_input_indices /* n_ctrl x 4 */) {
+  Handle* h = new Handle;
+  SystemConfig& sc = h->s.sc;
+  sc.plant = plant == 0 ? kParallel : kSerial;
+  sc.p = p;
+  sc.m = m;
+  sc.n_solver_iterations = n_iter;
+  sc.n_controllers = n_controllers;
+  for (int i = 0; i < 4; ++i) sc.delays[i] = delays[i];
+  for (int c = 0; c < n_controllers; ++c) {
+    ControllerConfig& cc = sc.ctrl[c];
+    cc.n_sub_control_inputs = n_sub_control_inputs[c];
+    cc.n_controlled_outputs = n_controlled_outputs[c];
+    for (int i = 0; i < 4; ++i) {
+      cc.controlled_output_indices[i] = controlled_output_indices[c * 4 + i];
+      cc.control_input_indices[i] = control_input_indices[c * 4 + i];
+      // a controller that is not "reduced" keeps the system order (aug_lin_sys.cc:158)
+      cc.delays[i] = cc.n_sub_control_inputs == 4 ? delays[i] : delays[cc.control_input_indices[i]];
+    }
+  }
+  return FinishCreate(h);
+}
+
+static void* FinishCreate(Handle* h) {
   Plant pl(h->s.sc.plant);
   const int n_obs = pl.n_states + h->s.sc.n_disturbance_states;
   std::memset(h->s.uwt, 0, sizeof h->s.uwt);
   std::memset(h->s.ywt, 0, sizeof h->s.ywt);
   for (int i = 0; i < 4; ++i) h->s.uwt[i * 4 + i] = 1;
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < kMaxControllers; ++c) {
     const int ny = h->s.sc.ctrl[c].n_controlled_outputs;
     for (int i = 0; i < ny; ++i) h->s.ywt[c][i * ny + i] = 1;
     for (int i = 0; i < 4; ++i) {

@@ -56,7 +56,16 @@ struct ControllerConfig {
   int control_input_indices[4] = {0, 1, 2, 3};  // permutation of system control inputs
   int n_controlled_outputs = 3;
   int controlled_output_indices[4] = {0, 1, 3, 0};
+  // The Delays template argument of this controller's AugmentedLinearizedSystem, by LOCAL input
+  // position (aug_lin_sys.h:34-40, aug_lin_sys.cc:156-173).  The reference's two plants hand the
+  // same ConstexprArray<0,40,0,40> to every sub-controller because their permutations map delayed
+  // inputs onto delayed inputs; a configuration with unequal delays instantiates each
+  // AugmentedLinearizedSystem with the delays of its own input order.  delays[0] < 0: use
+  // SystemConfig::delays as they are (the reference's own instantiations).
+  int delays[4] = {-1, -1, -1, -1};
 };
+
+constexpr int kMaxControllers = 4;   // NerveCenter takes a parameter pack of any size (nerve_center.h:19-38)
 
 struct SystemConfig {
   PlantKind plant = kParallel;
@@ -66,7 +75,7 @@ struct SystemConfig {
   double Ts = 0.05;
   int n_controllers = 2;
   int n_solver_iterations = 9;
-  ControllerConfig ctrl[2];
+  ControllerConfig ctrl[kMaxControllers];
 };
 
 // ---------------------------------------------------------------------------
@@ -100,10 +109,10 @@ class AugLinSys {
     n_delay_states = 0;
     n_delayed_inputs = 0;
     for (int i = 0; i < 4; ++i) {
-      n_delay_[i] = sc.delays[i];
+      n_delay_[i] = cc.delays[0] < 0 ? sc.delays[i] : cc.delays[i];
       ctrl_idx_[i] = cc.control_input_indices[i];
-      n_delay_states += sc.delays[i];
-      if (sc.delays[i] != 0) n_delayed_inputs++;
+      n_delay_states += n_delay_[i];
+      if (n_delay_[i] != 0) n_delayed_inputs++;
     }
     n_sub_control_inputs = cc.n_sub_control_inputs;
     is_reduced = n_sub_control_inputs != n_control_inputs;

@@ -29,6 +29,7 @@ def lib():
         _LIB = C.CDLL(str(so))
         _LIB.orc_create.restype = C.c_void_p
         _LIB.orc_create.argtypes = [C.c_int] * 4
+        _LIB.orc_create_config.restype = C.c_void_p
         for name in ("orc_destroy", "orc_set_weights", "orc_set_constraints", "orc_set_observer_gain",
                      "orc_set_output_reference", "orc_initialize", "orc_get_next_input",
                      "orc_get_linearization", "orc_get_prediction", "orc_get_qp",
@@ -64,6 +65,40 @@ class Oracle:
                                   _p(f64(setup.rate_lower)), _p(f64(setup.rate_upper)))
         yref = f64(np.tile(np.asarray(setup.yref, dtype=np.float64), (p, 1)))
         L.orc_set_output_reference(self.h, _p(yref))
+
+    @classmethod
+    def from_configuration(cls, conf, uwt, ywts, constraints, yref):
+        """A general configuration (compressor_mpc_b200.Configuration): uwt full 4 x 4, ywts one matrix
+        per sub-controller, constraints one (lower, upper, rate_lower, rate_upper) per sub-controller,
+        yref (4,) or (p, 4)."""
+        L = lib()
+        self = cls.__new__(cls)
+        self.setup, self.p = None, conf.p
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        nc = len(conf.controllers)
+        outs = np.zeros((nc, 4), dtype=np.int32)
+        for c, sc in enumerate(conf.controllers):
+            outs[c, :len(sc.controlled_outputs)] = sc.controlled_outputs
+        self.h = C.c_void_p(L.orc_create_config(
+            C.c_int(conf.plant), C.c_int(conf.p), C.c_int(conf.m), C.c_int(conf.n_iterations), _p(i32(conf.delays)),
+            C.c_int(nc), _p(i32([sc.n_inputs for sc in conf.controllers])),
+            _p(i32([len(sc.controlled_outputs) for sc in conf.controllers])), _p(outs),
+            _p(i32(conf.input_permutations()))))
+        self.n = L.orc_n_states(self.h)
+        self.n_in = L.orc_n_inputs(self.h)
+        self.n_ctrl = nc
+        self.nu = conf.controllers[0].n_inputs
+        self.ny = [len(sc.controlled_outputs) for sc in conf.controllers]
+        uwt = f64(uwt)
+        for c in range(nc):
+            L.orc_set_weights(self.h, c, _p(uwt), _p(f64(ywts[c])))
+            lo, up, rlo, rup = constraints[c]
+            L.orc_set_constraints(self.h, c, _p(f64(lo)), _p(f64(up)), _p(f64(rlo)), _p(f64(rup)))
+        yref = f64(yref)
+        if yref.ndim == 1:
+            yref = f64(np.tile(yref, (conf.p, 1)))
+        L.orc_set_output_reference(self.h, _p(yref))
+        return self
 
     def __del__(self):
         try:

