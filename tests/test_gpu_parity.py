@@ -398,9 +398,12 @@ def test_shortest_and_longest_horizons_and_rejected_configurations(setups, pkg, 
         assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U, p
         assert np.array_equal(g["active"], o["active"]), p
     C = pkg.capi
+    # (other move horizons, delays and output partitions are served by the general path since round 2:
+    # tests/test_generic_config.py)
     for mutate in (lambda c: setattr(c, "p", 257), lambda c: setattr(c, "p", 1), lambda c: setattr(c, "batch", 0),
-                   lambda c: setattr(c, "m", 3), lambda c: c.delays.__setitem__(1, 20),
-                   lambda c: setattr(c, "n_controllers", 3), lambda c: c.n_controlled_outputs.__setitem__(1, 2)):
+                   lambda c: setattr(c, "m", 5), lambda c: c.delays.__setitem__(1, 1),
+                   lambda c: setattr(c, "n_controllers", 3), lambda c: setattr(c, "n_disturbance_states", 2),
+                   lambda c: c.n_controlled_outputs.__setitem__(1, 5)):
         cfg = C.default_config(0, 1, 4)
         mutate(cfg)
         h = C.C.c_void_p()
@@ -861,7 +864,9 @@ def test_timing_window_leaves_the_results_alone(case, setups, pkg, gpu_lib):
         y = ref["traj"][:, k, 5 + len(x_def):]
         u, ns = nc.GetNextInputWithTiming(y, 2)
         assert np.array_equal(u, nc2.GetNextInput(y)) and ns > 0
-        assert np.array_equal(u, ref["traj"][:, k, 1 + len(x_def):5 + len(x_def)])
+        # (the closed loop linearises inside its plant kernel, the host-facing step in lin_kernel: same
+        # numbers to rounding, not to the bit)
+        assert np.allclose(u, ref["traj"][:, k, 1 + len(x_def):5 + len(x_def)], rtol=1e-9, atol=1e-12)
 
 
 def test_run_all_tests_workflow(setups, golden, pkg, gpu_lib, tmp_path):

@@ -34,6 +34,9 @@ conf = pkg.Configuration(0, [pkg.SubController(1, [0, 3]), pkg.SubController(1, 
                          m=3, p=40, delays=(0, 6, 0, 9), n_iterations=3)
 nc = pkg.NerveCenter.from_configuration(conf, batch=B)
 nc.SetOutputReference(np.asarray(s.yref))
+nc.SetWeights(s.uwt, [np.diag([1.0, 420.0])] * 3)
+for c, sl in enumerate((slice(0, 1), slice(1, 2), slice(0, 2))):
+    nc.SetConstraints(c, pkg.InputConstraints(s.lower[sl], s.upper[sl], s.rate_lower[sl], s.rate_upper[sl]))
 x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, 12)
 r = nc.run_closed_loop(x0, be, bo, 12)
 print("general", "ok", np.isfinite(r["traj"]).all(), int(r["status"].max()))
