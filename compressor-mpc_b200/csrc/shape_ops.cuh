@@ -37,7 +37,7 @@ AssembleFn assemble_variant(int p) {
 
 template <class S>
 int shape_setup(cmpc_handle* h) {
-  const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow);
+  const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow, stage_tiles_for(h->P.p));
   h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 8);
 #ifdef CMPC_PHASE_TIMING
   if (const char* e = getenv("CMPC_DEBUG_SMEM_MIN")) { size_t m = size_t(atol(e)); if (h->smem_bytes < m) h->smem_bytes = m; }  // occupancy experiments

@@ -64,6 +64,17 @@ constexpr int kRing = kDelay - 1;   // slots of one delay ring (the head is kept
 constexpr int kMaxStageTilesLadder = 18;  // squaring (2) + up to 16 blocks x 6 columns / 8 per giant-step stage
 constexpr int kMaxPow = 8;           // stages of the power ladder: horizons up to 8 * 2^5 = 256
 constexpr int kMaxStageTiles = 20;  // E tiles one warp may keep in registers (aliased E)
+// The 2x horizon of the sweep (p = 200) runs with 3 CTAs per SM instead of 4: that leaves 168 registers
+// per thread, enough to keep all 27 (36 for four outputs) table tiles of a warp in registers, so the
+// table can overwrite its own inputs there as well (65 KB of shared memory per CTA instead of 100 KB,
+// which allowed only 2 CTAs per SM and spilled at 128 registers).
+#ifdef CMPC_P200_LEGACY   // the round-1 layout, kept for A/B measurements
+__host__ __device__ constexpr int stage_tiles_for(int) { return kMaxStageTiles; }
+__host__ __device__ constexpr int assemble_min_blocks(int) { return 4; }
+#else
+__host__ __device__ constexpr int stage_tiles_for(int p) { return p == 200 ? 36 : kMaxStageTiles; }
+__host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : 4; }
+#endif
 
 // offsets inside one controller's global state record
 constexpr int kOffXhat = 0, kOffDx = 16, kOffYold = 112, kOffUold = 116;
@@ -128,6 +139,11 @@ struct DeviceState {
 // visible; pdl_trigger() tells the scheduler that this CTA no longer minds company.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#ifndef CMPC_NO_SOLVE_PREFETCH
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 
 __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
@@ -167,7 +183,7 @@ template <class S>
 struct SmemLayout {
   int yv, dxd, q, Cc, BF, carry, U, cz, region, L, R, V, lr_end, E, ldE, total;
   bool e_alias;
-  __host__ __device__ SmemLayout(int p, int b_max, int n_pow) {
+  __host__ __device__ SmemLayout(int p, int b_max, int n_pow, int max_stage_tiles) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     yv = take(4);
@@ -189,7 +205,7 @@ struct SmemLayout {
     // L, R, V when every warp can hold its output tiles in registers; for longer horizons L, R, V
     // are placed behind it.
     const int n_nt = (giant_cols(b_max, full_blocks(p, b_max)) + 7) / 8;
-    e_alias = (n_nt + S::WPC - 1) / S::WPC <= kMaxStageTiles / S::NY;
+    e_alias = (n_nt + S::WPC - 1) / S::WPC <= max_stage_tiles / S::NY;
     E = region;
     L = region + ((e_alias || n_scr > e_size) ? n_scr : e_size);
     R = L + kBaby * S::NY * kLD;
@@ -499,7 +515,7 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 // every tile count, stride and loop bound below then folds to a constant.  PCT = 0 reads them
 // from the parameters.
 template <class S, int RPT, int PCT>
-__global__ void __launch_bounds__(S::NCTRL * S::TPC, CMPC_MIN_BLOCKS)
+__global__ void __launch_bounds__(S::NCTRL * S::TPC, assemble_min_blocks(PCT))
 assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
   pdl_wait();
@@ -529,7 +545,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int b_full = CT ? kBfullCt : P.b_full;
   const int r_cols_all = giant_cols(b_max, b_full);   // columns of R
   const int ldr = CT ? giant_stride(giant_cols(kBmaxCt, kBfullCt)) : P.ldr, n_pow = CT ? ladder_stages(kBmaxCt) : P.n_pow;
-  const SmemLayout<S> lay(p, b_max, n_pow);
+  constexpr int kStageTiles = stage_tiles_for(PCT);
+  const SmemLayout<S> lay(p, b_max, n_pow, kStageTiles);
   const int ldE = lay.ldE;
   double* sm = smem + g * lay.total;
   const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
@@ -887,7 +904,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
     }
     if (lay.e_alias) {
-      constexpr int MAXNT = kMaxStageTiles / NY;   // column blocks per warp held in registers
+      constexpr int MAXNT = kStageTiles / NY;   // column blocks per warp held in registers
       double acc[MAXNT][NY][2];
 #pragma unroll
       for (int i = 0; i < MAXNT; ++i) {
@@ -1210,6 +1227,17 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen) * 2 + c;
     double* plan = G.work + rec * kWorkStride + kWPlan;
+    if constexpr (MODE == 0) {
+      // what the a-priori update at the very end reads (three lines of the hand-over record, the
+      // delay-ring slots and u_old): asked for now, they are in L1 when the sweeps are done
+      const double* wb = G.work + rec * kWorkStride + kWBF;
+      const double* gsp = G.ctrl + rec * kCtrlStateStride;
+      prefetch_l1(wb);
+      prefetch_l1(wb + 16);
+      prefetch_l1(wb + 32);
+      prefetch_l1(gsp + kOffDx + S::NOBS + 2 + P.ring_pos);
+      prefetch_l1(gsp + kOffDx + S::NOBS + 2 + kRing + P.ring_pos);
+    }
     if constexpr (MODE == 2) {
       double zf[4];
 #pragma unroll
