@@ -116,7 +116,6 @@ __device__ bool dopri5_try_step_pair(unsigned full, int c, const double uc[4], d
   const double h = *dt;
   double k2[6], k3[6], k4[6], k5[6], k6[6], k7[6], xt[6], xn[6];
   xt[5] = xn[5] = 0.0;
-#ifdef CMPC_DOPRI_UNROLLED   // the round-1 form, kept for A/B measurements
 #pragma unroll
   for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * b21 * k1[i];
   pair_derivative<PLANT>(full, c, xt, uc, u_tank, k2);
@@ -137,60 +136,6 @@ __device__ bool dopri5_try_step_pair(unsigned full, int c, const double uc[4], d
   for (int i = 0; i < NS; ++i)
     xn[i] = xs[i] + h * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
   pair_derivative<PLANT>(full, c, xn, uc, u_tank, k7);
-#else
-#pragma unroll
-  for (int i = 0; i < 6; ++i) k2[i] = k3[i] = k4[i] = k5[i] = k6[i] = k7[i] = 0.0;
-  // The six stages share ONE copy of the derivative code: the loop is kept rolled on purpose.  This
-  // warp is alone on its scheduler, and with the stages unrolled (six inlined derivatives, 29 KB of
-  // straight-line code per step) it spent most of its time waiting for instruction fetches
-  // (ncu: stall_no_instruction 8.9 per issued instruction).  Every stage keeps its own expression,
-  // so the arithmetic is the one of the unrolled form, bit for bit.
-#pragma unroll 1
-  for (int s = 2; s <= 7; ++s) {
-    switch (s) {
-      case 2:
-#pragma unroll
-        for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * b21 * k1[i];
-        break;
-      case 3:
-#pragma unroll
-        for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b31 * k1[i] + b32 * k2[i]);
-        break;
-      case 4:
-#pragma unroll
-        for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b41 * k1[i] + b42 * k2[i] + b43 * k3[i]);
-        break;
-      case 5:
-#pragma unroll
-        for (int i = 0; i < NS; ++i) xt[i] = xs[i] + h * (b51 * k1[i] + b52 * k2[i] + b53 * k3[i] + b54 * k4[i]);
-        break;
-      case 6:
-#pragma unroll
-        for (int i = 0; i < NS; ++i)
-          xt[i] = xs[i] + h * (b61 * k1[i] + b62 * k2[i] + b63 * k3[i] + b64 * k4[i] + b65 * k5[i]);
-        break;
-      default:
-#pragma unroll
-        for (int i = 0; i < NS; ++i)
-          xt[i] = xs[i] + h * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
-        break;
-    }
-    double kk[6];
-    pair_derivative<PLANT>(full, c, xt, uc, u_tank, kk);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      if (s == 2) k2[i] = kk[i];
-      else if (s == 3) k3[i] = kk[i];
-      else if (s == 4) k4[i] = kk[i];
-      else if (s == 5) k5[i] = kk[i];
-      else if (s == 6) k6[i] = kk[i];
-      else {
-        k7[i] = kk[i];
-        xn[i] = xt[i];
-      }
-    }
-  }
-#endif
   // squared scaled errors of this lane's states; summed in plant state order 0..N-1
   double e2[6];
 #pragma unroll

@@ -73,7 +73,11 @@ __host__ __device__ constexpr int stage_tiles_for(int) { return kMaxStageTiles; 
 __host__ __device__ constexpr int assemble_min_blocks(int) { return 4; }
 #else
 __host__ __device__ constexpr int stage_tiles_for(int p) { return p == 200 ? 36 : kMaxStageTiles; }
+#ifdef CMPC_P100_OCC5
+__host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : (pct == 100 ? 5 : 4); }
+#else
 __host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : 4; }
+#endif
 #endif
 
 // offsets inside one controller's global state record
@@ -139,11 +143,6 @@ struct DeviceState {
 // visible; pdl_trigger() tells the scheduler that this CTA no longer minds company.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-#ifndef CMPC_NO_SOLVE_PREFETCH
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
 
 __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
@@ -181,7 +180,7 @@ __host__ __device__ constexpr int ladder_stages(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int yv, dxd, q, Cc, BF, carry, U, cz, region, L, R, V, lr_end, E, ldE, total;
+  int yv, dxd, q, Cc, BF, carry, U, cz, mbar, region, L, R, V, lr_end, E, ldE, total;
   bool e_alias;
   __host__ __device__ SmemLayout(int p, int b_max, int n_pow, int max_stage_tiles) {
     int o = 0;
@@ -194,6 +193,7 @@ struct SmemLayout {
     carry = take(S::WPC * S::NSC);
     U = take(6 * kLD);
     cz = take(kDelay * S::NY);
+    mbar = take(2);   // transaction barrier of the bulk-copy staging (CMPC_TMA_STAGING builds)
     region = o;
     const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then Ad^(2^j)
     // E is channel-major: E[(y kNC + c) ldE + r].  ldE = 2 mod 4 keeps the 16-byte row-pair loads of
@@ -566,12 +566,36 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // all global loads are issued first so that they are in flight together
   constexpr int NLD = (kNNP + TPC - 1) / TPC;
   double a_v[NLD], x_v[NLD], q_v[2], cc_v = 0.0, yd_v = 0.0;
+#ifdef CMPC_TMA_STAGING
+  // Experiment (BASELINE north_star: "H/A/b staged in shared memory via TMA"): the three dense pieces
+  // of the hand-over record (A, [B|f], C: 2.6 KB) come in as bulk asynchronous copies that complete
+  // on a transaction barrier (cp.async.bulk = UBLKCP in SASS) instead of ld.global -> st.shared.
+  const unsigned mbar_s = unsigned(__cvta_generic_to_shared(sm + lay.mbar));
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  group_sync(g, TPC);
+  if (t == 0) {
+    constexpr unsigned kBytesA = kNNP * 8, kBytesC = 4 * N * 8;
+    static_assert(kBytesA % 16 == 0 && kBytesC % 16 == 0, "bulk copies move multiples of 16 bytes");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(2 * kBytesA + kBytesC) : "memory");
+    auto bulk = [&](double* dst, const double* src, unsigned bytes) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src), "r"(bytes), "r"(mbar_s) : "memory");
+    };
+    bulk(Ac, wk + kWAc, kBytesA);
+    bulk(Xc, wk + kWXc, kBytesA);
+    bulk(Cc, wk + kWCc, kBytesC);
+  }
+#else
 #pragma unroll
   for (int k = 0; k < NLD; ++k) {
     const int i = t + k * TPC;
     a_v[k] = (i < kNNP) ? wk[kWAc + i] : 0.0;
     x_v[k] = (i < kNNP) ? wk[kWXc + i] : 0.0;
   }
+#endif
   // delay-line contents relative to u_old (AdjustAllDelayedStates, aug_lin_sys.h:141-154)
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -584,12 +608,15 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       q_v[k] = gs[kOffDx + slot] - gs[kOffUold + 1 + 2 * d];
     }
   }
+#ifndef CMPC_TMA_STAGING
   if (t < 4 * N) cc_v = wk[kWCc + t];
+#endif
   if (t < 4) yd_v = y[size_t(scen) * 4 + t];
   else if (t < 8) yd_v = gs[kOffDx + N + t - 4];
   // Zero padding without clearing the region: the hand-over record arrives zero-padded, every
   // product below stores all kLD rows/columns of its result (a pad row of A or pad column of B gives
   // an exact zero), and the pads of the three seeds (L, R, V) are cleared where they are planted.
+#ifndef CMPC_TMA_STAGING
 #pragma unroll
   for (int k = 0; k < NLD; ++k) {
     const int i = t + k * TPC;
@@ -598,10 +625,22 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       Xc[i] = x_v[k];
     }
   }
+  if (t < 4 * N) Cc[t] = cc_v;
+#else
+  (void)a_v; (void)x_v; (void)cc_v;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CMPC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra CMPC_DONE;\n"
+      "bra CMPC_WAIT;\n"
+      "CMPC_DONE:\n"
+      "}\n" ::"r"(mbar_s) : "memory");
+#endif
 #pragma unroll
   for (int k = 0; k < 2; ++k)
     if (t + k * TPC < 2 * kDelay) q[t + k * TPC] = q_v[k];
-  if (t < 4 * N) Cc[t] = cc_v;
   if (t < 4) yv[t] = yd_v;
   else if (t < 8) dxd[t - 4] = yd_v;
   group_sync(g, TPC);
@@ -1227,17 +1266,6 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen) * 2 + c;
     double* plan = G.work + rec * kWorkStride + kWPlan;
-    if constexpr (MODE == 0) {
-      // what the a-priori update at the very end reads (three lines of the hand-over record, the
-      // delay-ring slots and u_old): asked for now, they are in L1 when the sweeps are done
-      const double* wb = G.work + rec * kWorkStride + kWBF;
-      const double* gsp = G.ctrl + rec * kCtrlStateStride;
-      prefetch_l1(wb);
-      prefetch_l1(wb + 16);
-      prefetch_l1(wb + 32);
-      prefetch_l1(gsp + kOffDx + S::NOBS + 2 + P.ring_pos);
-      prefetch_l1(gsp + kOffDx + S::NOBS + 2 + kRing + P.ring_pos);
-    }
     if constexpr (MODE == 2) {
       double zf[4];
 #pragma unroll
