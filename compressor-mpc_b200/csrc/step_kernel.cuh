@@ -73,11 +73,7 @@ __host__ __device__ constexpr int stage_tiles_for(int) { return kMaxStageTiles; 
 __host__ __device__ constexpr int assemble_min_blocks(int) { return 4; }
 #else
 __host__ __device__ constexpr int stage_tiles_for(int p) { return p == 200 ? 36 : kMaxStageTiles; }
-#ifdef CMPC_P100_OCC5
-__host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : (pct == 100 ? 5 : 4); }
-#else
 __host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : 4; }
-#endif
 #endif
 
 // offsets inside one controller's global state record
@@ -193,7 +189,7 @@ struct SmemLayout {
     carry = take(S::WPC * S::NSC);
     U = take(6 * kLD);
     cz = take(kDelay * S::NY);
-    mbar = take(2);   // transaction barrier of the bulk-copy staging (CMPC_TMA_STAGING builds)
+    mbar = take(2);   // transaction barrier of the bulk-copy staging
     region = o;
     const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then Ad^(2^j)
     // E is channel-major: E[(y kNC + c) ldE + r].  ldE = 2 mod 4 keeps the 16-byte row-pair loads of
@@ -566,10 +562,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // all global loads are issued first so that they are in flight together
   constexpr int NLD = (kNNP + TPC - 1) / TPC;
   double a_v[NLD], x_v[NLD], q_v[2], cc_v = 0.0, yd_v = 0.0;
-#ifdef CMPC_TMA_STAGING
-  // Experiment (BASELINE north_star: "H/A/b staged in shared memory via TMA"): the three dense pieces
-  // of the hand-over record (A, [B|f], C: 2.6 KB) come in as bulk asynchronous copies that complete
-  // on a transaction barrier (cp.async.bulk = UBLKCP in SASS) instead of ld.global -> st.shared.
+#ifndef CMPC_NO_TMA_STAGING
+  // The three dense pieces of the hand-over record (A, [B|f], C: 2.6 KB) come in as bulk asynchronous
+  // copies (TMA, cp.async.bulk = UBLKCP in SASS) that complete on a transaction barrier, instead of
+  // ld.global -> registers -> st.shared.  Measured neutral at p = 100 (103.0 vs 103.1 us per launch)
+  // and 1 % faster at p = 200 (2484 vs 2508 us); CMPC_NO_TMA_STAGING builds the register path.
   const unsigned mbar_s = unsigned(__cvta_generic_to_shared(sm + lay.mbar));
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
@@ -608,7 +605,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       q_v[k] = gs[kOffDx + slot] - gs[kOffUold + 1 + 2 * d];
     }
   }
-#ifndef CMPC_TMA_STAGING
+#ifdef CMPC_NO_TMA_STAGING
   if (t < 4 * N) cc_v = wk[kWCc + t];
 #endif
   if (t < 4) yd_v = y[size_t(scen) * 4 + t];
@@ -616,7 +613,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // Zero padding without clearing the region: the hand-over record arrives zero-padded, every
   // product below stores all kLD rows/columns of its result (a pad row of A or pad column of B gives
   // an exact zero), and the pads of the three seeds (L, R, V) are cleared where they are planted.
-#ifndef CMPC_TMA_STAGING
+#ifdef CMPC_NO_TMA_STAGING
 #pragma unroll
   for (int k = 0; k < NLD; ++k) {
     const int i = t + k * TPC;
