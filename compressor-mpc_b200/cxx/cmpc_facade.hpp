@@ -56,6 +56,12 @@ class NerveCenter : public ControllerInterface {
     Check(cmpc_plant_dims(plant, &n_states_, &n_inputs_));
     Check(cmpc_create(&cfg_, device, &h_));
   }
+  /// A configuration outside the reference's own instantiations (cmpc_config filled by hand: other
+  /// delays, move horizon, output partitions, up to four sub-controllers; see include/cmpc.h).
+  explicit NerveCenter(const cmpc_config& cfg, int device = 0) : cfg_(cfg) {
+    Check(cmpc_plant_dims(cfg.plant, &n_states_, &n_inputs_));
+    Check(cmpc_create(&cfg_, device, &h_));
+  }
   ~NerveCenter() override { cmpc_destroy(h_); }
   NerveCenter(const NerveCenter&) = delete;
   NerveCenter& operator=(const NerveCenter&) = delete;
@@ -71,8 +77,8 @@ class NerveCenter : public ControllerInterface {
   /// uwt: full 4 x 4 input weight; ywts[c]: n_y x n_y output weight of sub-controller c
   /// (tuple overload, nerve_center.h:113-116; the sub-matrix of uwt is taken as in :225-234).
   void SetWeights(const double* uwt, const std::vector<std::vector<double>>& ywts) {
-    const int nu = cfg_.n_sub_control_inputs;
     for (int c = 0; c < cfg_.n_controllers; ++c) {
+      const int nu = cfg_.n_sub_control_inputs_per[c] ? cfg_.n_sub_control_inputs_per[c] : cfg_.n_sub_control_inputs;
       std::vector<double> sub(nu * nu);
       for (int i = 0; i < nu; ++i)
         for (int j = 0; j < nu; ++j)

@@ -71,6 +71,69 @@ def run(seed: int, n_cfg: int, verbose: bool = False):
     return bad
 
 
+def run_general(seed: int, n_cfg: int, verbose: bool = False):
+    """Random GENERAL configurations on the GPU's general path against the generalised
+    oracle: plant, number of sub-controllers and their input counts, controlled-output partitions,
+    per-input delays (0 or 2..60), move horizon, prediction horizon, sweep count."""
+    pkg = ge.load_package()
+    setups = {k: pkg.setupfile.setup_from_dict(v)
+              for k, v in json.load(open(ROOT / "tests" / "golden" / "setups.json")).items()}
+    rng = np.random.default_rng(seed)
+    splits = [[4], [2, 2], [1, 3], [3, 1], [1, 1, 2], [2, 1, 1], [1, 2, 1], [1, 1, 1, 1]]
+    bad = []
+    for it in range(n_cfg):
+        plant = int(rng.integers(0, 2))
+        base = setups["coop-par" if plant == 0 else "coop-ser"]
+        nus = splits[rng.integers(len(splits))]
+        m = int(rng.integers(1, 5))
+        while m * max(nus) > 8:
+            m -= 1
+        p = int(rng.choice([rng.integers(m, 12), rng.integers(12, 70), rng.integers(70, 200)]))
+        delays = [int(rng.choice([0, rng.integers(2, 61)])) for _ in range(4)]
+        ctrls, ywts, cons, first = [], [], [], 0
+        for nu in nus:
+            ny = int(rng.integers(1, 5))
+            outs = [int(v) for v in rng.permutation(4)[:ny]]
+            ctrls.append(pkg.SubController(nu, outs))
+            ywts.append(np.diag(rng.choice([1.0, 10.0, 420.0], ny)))
+            idx = [(first + i) % 2 for i in range(nu)]          # torque / recycle bounds of the setup, by input kind
+            cons.append(tuple(np.asarray(getattr(base, k))[idx] * rng.uniform(0.3, 1.0)
+                              for k in ("lower", "upper", "rate_lower", "rate_upper")))
+            first += nu
+        conf = pkg.Configuration(plant, ctrls, p=p, m=m, delays=delays, n_iterations=int(rng.integers(1, 7)))
+        x_def, _ = ol.plant_defaults(plant)
+        n = len(x_def)
+        B, T = int(rng.integers(1, 4)), int(rng.integers(30, 110))
+        x0, be, bo = pkg.scenarios.make_scenarios(base, x_def, B, T, first=int(rng.integers(0, 1000)))
+        be[:, 0] = rng.integers(5, T)
+        nc = pkg.NerveCenter.from_configuration(conf, batch=B)
+        nc.SetWeights(base.uwt, ywts)
+        nc.SetOutputReference(np.asarray(base.yref, dtype=np.float64))
+        for c, k in enumerate(cons):
+            nc.SetConstraints(c, pkg.InputConstraints(*k))
+        g = nc.run_closed_loop(x0, be, bo, T)
+        o = ol.Oracle.from_configuration(conf, base.uwt, ywts, cons, base.yref).run_closed_loop(x0, be, bo, T, n_threads=3)
+        fin = np.isfinite(o["traj"]).all(axis=2).all(axis=0)
+        K = T if fin.all() else max(int(np.argmin(fin)) - 3, 0)
+        ug, uo = g["traj"][:, :K, 1 + n:5 + n], o["traj"][:, :K, 1 + n:5 + n]
+        err = float(np.max(np.abs(ug - uo) / np.maximum(np.abs(uo), 1e-3))) if K else 0.0
+        ok = (err < 1e-6 and np.array_equal(g["active"][:, :K], o["active"][:, :K])
+              and np.array_equal(g["status"][:, :K] != 0, o["status"][:, :K] != 0))
+        cfg = dict(plant=plant, nus=nus, m=m, p=p, delays=delays, outs=[c.controlled_outputs for c in ctrls],
+                   n_iter=conf.n_iterations, B=B, T=T)
+        if verbose:
+            print(it, cfg, "K", K, "err", err, "ok", ok, flush=True)
+        if not ok:
+            bad.append(dict(cfg, K=K, err=err))
+        nc.close()
+    return bad
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[3] == "general":
+        b = run_general(int(sys.argv[1]), int(sys.argv[2]), verbose=True)
+        print(f"{len(b)} mismatches", b)
+        raise SystemExit
+
     b = run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 40, verbose=True)
     print(f"{len(b)} mismatches", b)

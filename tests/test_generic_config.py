@@ -135,3 +135,32 @@ def test_generalised_oracle_reduces_to_the_reference_configuration(setups, pkg):
         cons = [(s.lower, s.upper, s.rate_lower, s.rate_upper)] * s.n_controllers
         r = ol.Oracle.from_configuration(conf, s.uwt, s.ywt, cons, s.yref).run_closed_loop(x_def, be, s.sim_offsets[None], T)
         assert np.array_equal(r["traj"], ref["traj"]) and np.array_equal(r["active"], ref["active"])
+
+
+@pytest.mark.gpu
+def test_random_general_configurations(pkg, gpu_lib):
+    """25 random general configurations (tests/fuzz_parity.py run_general): plant x controller split x
+    output partitions x delays x move and prediction horizons x sweep counts, against the oracle."""
+    import fuzz_parity
+    assert fuzz_parity.run_general(seed=11, n_cfg=25) == []
+
+
+@pytest.mark.gpu
+def test_general_path_through_the_other_entry_points(setups, pkg, gpu_lib):
+    """The general path behind the streaming host API and the timing window (there the window is the
+    whole step: one kernel does it)."""
+    s, conf, ywts, cons = general_cases(pkg, setups)["three-controllers"]
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 2, 40
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = [12, 20]
+    ref = build(pkg, conf, s, ywts, cons, B).run_closed_loop(x0, be, bo, T)
+    timed = build(pkg, conf, s, ywts, cons, B).run_closed_loop(x0, be, bo, T, n_timing_iterations=2)
+    assert np.array_equal(timed["traj"], ref["traj"]) and (timed["step_ns"] > 0).all()
+    nc = build(pkg, conf, s, ywts, cons, B)
+    nc.closed_loop_start(x0)
+    for k in range(T):
+        off = np.stack([bo[b, min(int((k >= be[b]).sum()), be.shape[1] - 1)] for b in range(B)])
+        assert np.array_equal(nc.closed_loop_step(off), ref["traj"][:, k]), k
+    H, f, G = nc.qp(2, cross_term=False)
+    assert H.shape == (B, 4, 4) and np.allclose(H, np.swapaxes(H, 1, 2)) and (np.linalg.eigvalsh(H) > 0).all()
