@@ -164,3 +164,26 @@ def test_general_path_through_the_other_entry_points(setups, pkg, gpu_lib):
         assert np.array_equal(nc.closed_loop_step(off), ref["traj"][:, k]), k
     H, f, G = nc.qp(2, cross_term=False)
     assert H.shape == (B, 4, 4) and np.allclose(H, np.swapaxes(H, 1, 2)) and (np.linalg.eigvalsh(H) > 0).all()
+
+
+@pytest.mark.gpu
+def test_general_path_failed_qp_gives_zero_move(setups, pkg, gpu_lib):
+    """mpc_qp_solver.cc:66-69 on the general path: a sub-controller whose QP cannot be solved (here:
+    lower bound above upper bound) applies the zero move and reports a status, the others go on; same
+    records as the oracle."""
+    s, conf, ywts, cons = general_cases(pkg, setups)["three-controllers"]
+    cons = list(cons)
+    lo, up, rlo, rup = cons[1]
+    cons[1] = (np.asarray(up) + 0.2, np.asarray(up), rlo, rup)          # empty interval for sub-controller 1
+    x_def, _ = ol.plant_defaults(s.plant)
+    B, T = 2, 50
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 10
+    g = build(pkg, conf, s, ywts, cons, B).run_closed_loop(x0, be, bo, T)
+    o = ol.Oracle.from_configuration(conf, s.uwt, ywts, cons, s.yref).run_closed_loop(x0, be, bo, T, n_threads=2)
+    n = len(x_def)
+    assert (g["status"][:, :, 1] != 0).all() and (o["status"][:, :, 1] != 0).all()
+    assert (g["status"][:, :, [0, 2]] == 0).all()
+    assert (g["traj"][:, :, 1 + n + 1] == 0).all()                        # its input (system input 1) never moves
+    assert rel_err(g["traj"][:, :, 1 + n:5 + n], o["traj"][:, :, 1 + n:5 + n], ATOL_U / RTOL_U) < RTOL_U
+    assert np.array_equal(g["active"], o["active"])
