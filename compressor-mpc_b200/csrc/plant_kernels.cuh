@@ -317,8 +317,11 @@ __device__ __forceinline__ void advance_pair(int b, int c, unsigned pair_mask, i
 // observer gain leaves the state estimate alone (P.obs_states_free: the linearisation point then
 // does not depend on the measurement being produced), after it otherwise -- and finally warp 0
 // stores the observer state with the new measurement.
-template <class S>
-__global__ void __launch_bounds__(128)
+// MINB: resident blocks per SM the register allocation aims at.  1 (195 registers, 2 blocks per SM)
+// is the fastest single wave, which is what a batch of a few thousand scenarios is; batches of many
+// waves (the 65 536-scenario sweep: 14 waves) are bound by how many integrations an SM holds at once.
+template <class S, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, ClosedLoopArrays A, bool lin_next) {
   pdl_wait();
   pdl_trigger();   // single wave

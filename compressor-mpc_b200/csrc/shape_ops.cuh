@@ -8,6 +8,13 @@
 
 namespace cmpc {
 
+// batches from this size on run the plant kernel's higher-occupancy instantiation (more than three
+// waves of 16-scenario blocks at 2 blocks per SM)
+constexpr int kAdvanceBigBatch = 16384;
+#ifndef CMPC_ADV_BIG_MINB
+#define CMPC_ADV_BIG_MINB 3
+#endif
+
 // Launch with programmatic stream serialisation (see pdl_wait / pdl_trigger in step_kernel.cuh).
 template <class... KArgs, class... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
@@ -152,7 +159,10 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
       h->win_used += 4;
     }
     // plant side of record k, and the observer update + linearisation of record k + 1
-    CU(launch_pdl(cl_advance_kernel<S>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
+    if (B >= kAdvanceBigBatch)
+      CU(launch_pdl(cl_advance_kernel<S, CMPC_ADV_BIG_MINB>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
+    else
+      CU(launch_pdl(cl_advance_kernel<S, 1>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
     h->lin_ahead = true;
     h->launches++;
     t += h->cfg.Ts;

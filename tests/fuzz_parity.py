@@ -71,16 +71,14 @@ def run(seed: int, n_cfg: int, verbose: bool = False):
     return bad
 
 
-def run_general(seed: int, n_cfg: int, verbose: bool = False):
-    """Random GENERAL configurations (SURVEY 8 f-4) on the GPU's general path against the generalised
-    oracle: plant, number of sub-controllers and their input counts, controlled-output partitions,
-    per-input delays (0 or 2..60), move horizon, prediction horizon, sweep count."""
+def general_configs(seed: int, n_cfg: int):
+    """The random general configurations of run_general, as a generator (shared with the sensitivity
+    analysis below): yields (index, conf, base setup, ywts, constraints, x0, block_end, block_off, T)."""
     pkg = ge.load_package()
     setups = {k: pkg.setupfile.setup_from_dict(v)
               for k, v in json.load(open(ROOT / "tests" / "golden" / "setups.json")).items()}
     rng = np.random.default_rng(seed)
     splits = [[4], [2, 2], [1, 3], [3, 1], [1, 1, 2], [2, 1, 1], [1, 2, 1], [1, 1, 1, 1]]
-    bad = []
     for it in range(n_cfg):
         plant = int(rng.integers(0, 2))
         base = setups["coop-par" if plant == 0 else "coop-ser"]
@@ -102,10 +100,49 @@ def run_general(seed: int, n_cfg: int, verbose: bool = False):
             first += nu
         conf = pkg.Configuration(plant, ctrls, p=p, m=m, delays=delays, n_iterations=int(rng.integers(1, 7)))
         x_def, _ = ol.plant_defaults(plant)
-        n = len(x_def)
         B, T = int(rng.integers(1, 4)), int(rng.integers(30, 110))
         x0, be, bo = pkg.scenarios.make_scenarios(base, x_def, B, T, first=int(rng.integers(0, 1000)))
         be[:, 0] = rng.integers(5, T)
+        yield it, conf, base, ywts, cons, x0, be, bo, T
+
+
+def _healthy_prefix(o, g, T):
+    healthy = np.isfinite(o["traj"]).all(axis=2).all(axis=0) & (o["status"] == 0).all(axis=2).all(axis=0) \
+        & (g["status"] == 0).all(axis=2).all(axis=0)
+    return T if healthy.all() else max(int(np.argmin(healthy)) - 3, 0)
+
+
+def oracle_sensitivity(conf, base, ywts, cons, x0, be, bo, T, rel=1e-14):
+    """How much this closed loop amplifies a perturbation of the size of rounding errors: the oracle
+    against itself with the initial state moved by `rel` (relative).  Returns the largest relative
+    input difference (same measure as the parity check) over the healthy prefix."""
+    n = x0.shape[1]
+    mk = lambda: ol.Oracle.from_configuration(conf, base.uwt, ywts, cons, base.yref)
+    a = mk().run_closed_loop(x0, be, bo, T, n_threads=3)
+    b = mk().run_closed_loop(x0 * (1.0 + rel), be, bo, T, n_threads=3)
+    K = _healthy_prefix(a, b, T)
+    ua, ub = a["traj"][:, :K, 1 + n:5 + n], b["traj"][:, :K, 1 + n:5 + n]
+    return float(np.max(np.abs(ua - ub) / np.maximum(np.abs(ua), 1e-3))) if K else 0.0
+
+
+def run_general(seed: int, n_cfg: int, verbose: bool = False):
+    """Random GENERAL configurations (SURVEY 8 f-4) on the GPU's general path against the generalised
+    oracle: plant, number of sub-controllers and their input counts, controlled-output partitions,
+    per-input delays (0 or 2..60), move horizon, prediction horizon, sweep count.
+
+    Compared up to shortly before the first record that is not healthy on either side (a non-finite
+    state, or a QP the exact solver gives up on: random configurations do reach numerically hopeless
+    problems, e.g. an unstable linearisation raised to the 164th power makes H indefinite in floating
+    point, and which of two summation orders trips first is not a parity statement; the zero move on a
+    failed QP has its own test).  Tolerance: 1e-6 like everywhere else -- or, for a loop that amplifies
+    rounding noise itself, 100 times what the ORACLE shows against itself when its initial state is
+    moved by 1e-14 (long horizons with heavy output weights make H ill-conditioned: cond(H) times the
+    1e-13 of two summation orders)."""
+    pkg = ge.load_package()
+    bad = []
+    for it, conf, base, ywts, cons, x0, be, bo, T in general_configs(seed, n_cfg):
+        n = x0.shape[1]
+        B = x0.shape[0]
         nc = pkg.NerveCenter.from_configuration(conf, batch=B)
         nc.SetWeights(base.uwt, ywts)
         nc.SetOutputReference(np.asarray(base.yref, dtype=np.float64))
@@ -113,23 +150,22 @@ def run_general(seed: int, n_cfg: int, verbose: bool = False):
             nc.SetConstraints(c, pkg.InputConstraints(*k))
         g = nc.run_closed_loop(x0, be, bo, T)
         o = ol.Oracle.from_configuration(conf, base.uwt, ywts, cons, base.yref).run_closed_loop(x0, be, bo, T, n_threads=3)
-        # Compared up to shortly before the first record that is not healthy on either side: a
-        # non-finite state, or a QP the exact solver gives up on.  Random configurations do reach
-        # numerically hopeless problems (an unstable linearisation raised to the 164th power makes H
-        # indefinite in floating point); which of two summation orders trips first is not a parity
-        # statement.  (The zero move on a failed QP has its own test.)
-        healthy = np.isfinite(o["traj"]).all(axis=2).all(axis=0) & (o["status"] == 0).all(axis=2).all(axis=0) \
-            & (g["status"] == 0).all(axis=2).all(axis=0)
-        K = T if healthy.all() else max(int(np.argmin(healthy)) - 3, 0)
+        K = _healthy_prefix(o, g, T)
         ug, uo = g["traj"][:, :K, 1 + n:5 + n], o["traj"][:, :K, 1 + n:5 + n]
         err = float(np.max(np.abs(ug - uo) / np.maximum(np.abs(uo), 1e-3))) if K else 0.0
+        sens = None
         ok = err < 1e-6 and np.array_equal(g["active"][:, :K], o["active"][:, :K])
-        cfg = dict(plant=plant, nus=nus, m=m, p=p, delays=delays, outs=[c.controlled_outputs for c in ctrls],
-                   n_iter=conf.n_iterations, B=B, T=T)
-        if verbose:
-            print(it, cfg, "K", K, "err", err, "ok", ok, flush=True)
         if not ok:
-            bad.append(dict(cfg, K=K, err=err))
+            sens = oracle_sensitivity(conf, base, ywts, cons, x0, be, bo, T)
+            ok = err < 100.0 * sens      # the loop itself turns 1e-14 into `sens`
+        cfg = dict(plant=conf.plant, nus=[c.n_inputs for c in conf.controllers], m=conf.m, p=conf.p, delays=list(conf.delays),
+                   outs=[c.controlled_outputs for c in conf.controllers], n_iter=conf.n_iterations, B=B, T=T)
+        if verbose:
+            print(it, cfg, "K", K, "err", err, "oracle self-sensitivity", sens, "ok", ok, flush=True)
+        if not ok:
+            per_rec = np.max(np.abs(ug - uo) / np.maximum(np.abs(uo), 1e-3), axis=(0, 2)) if K else np.zeros(1)
+            prof = {int(k): float(per_rec[k]) for k in np.linspace(0, max(K - 1, 0), 8).astype(int)}
+            bad.append(dict(cfg, K=K, err=err, oracle_self_sensitivity=sens, err_by_record=prof))
         nc.close()
     return bad
 
