@@ -378,7 +378,7 @@ int cmpc_create(const cmpc_config* cfg, int device, cmpc_handle** out) {
     A(dalloc(&G.status, size_t(B) * NC));
     A(dalloc(&G.active, size_t(B) * NC));
     A(dalloc(&G.objective, size_t(B) * NC));
-    A(dalloc(&G.ticks, size_t(B) * 16));
+    A(dalloc(&G.ticks, size_t(B) * 32));
     A(dalloc(&h->d_yref, size_t(NC) * cfg->p * 4));
     A(dalloc(&h->d_ring, size_t(B) * 2 * kDelay));
   }
@@ -621,11 +621,11 @@ int cmpc_get_step_info(cmpc_handle* h, int32_t* status, uint32_t* active, double
   return CMPC_OK;
 }
 
-int cmpc_debug_phase_ticks(cmpc_handle* h, long long* out /* B x 16 */) {
+int cmpc_debug_phase_ticks(cmpc_handle* h, long long* out /* B x 32 */) {
   CMPC_ENTER(h);
   if (!out) return fail(CMPC_ERR_ARG, "null argument");
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpy(out, h->G.ticks, size_t(h->cfg.batch) * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, h->G.ticks, size_t(h->cfg.batch) * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
   return CMPC_OK;
 }
 

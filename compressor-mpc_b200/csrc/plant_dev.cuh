@@ -55,10 +55,52 @@ struct ValveD {
 
 __device__ __forceinline__ double sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
+// ---- straight-line square root and division for the plant integrator ---------------------------
+// sqrt() and / compile to a fast path plus a branch to a special-case routine each; the branches cut
+// the derivative into basic blocks, so its five independent sqrt / div chains run one after the
+// other.  The integrator is one warp per block in a one-wave kernel, i.e. bound by exactly that
+// dependent latency.  These forms are the fast path alone (hardware seed, two coupled Newton steps,
+// one residual correction with fused multiply-adds, which rounds like the IEEE operation for operands
+// in the normal range) and only RECORD in `bad` that an operand was outside [1e-290, 1e290]; the
+// caller then redoes the whole derivative with the standard operations (never in a sane plant state).
+__device__ __forceinline__ double sqrt_inrange(double x, bool& bad) {
+  bad |= !(x >= 1e-290 && x <= 1e290);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  return fma(fma(-g, g, x), h, g);
+}
+__device__ __forceinline__ double div_inrange(double a, double b, bool& bad) {
+  bad |= !(fabs(b) >= 1e-290 && fabs(b) <= 1e290 && fabs(a) <= 1e290 && (fabs(a) >= 1e-290 || a == 0.0));
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+  double e = fma(-b, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-b, y, 1.0);
+  y = fma(y, e, y);
+  const double q = a * y;
+  return fma(fma(-b, q, a), y, q);
+}
+
 // valve_eqs.h:39-52
 template <class V>
 __device__ __forceinline__ double valve_mass_flow(double p_in, double p_out, double u, double m_offset) {
   const double dp = 10.0 * sqrt(fabs(p_in - p_out)) * sgn(p_in - p_out);
+  const double u2 = u * u, u3 = u2 * u;
+  const double poly_dp = V::c(0) * u3 + V::c(1) * u2 + V::c(2) * u + V::c(3);
+  const double poly_0 = V::c(4) * u3 + V::c(5) * u2 + V::c(6) * u + V::c(7);
+  return dp * poly_dp + poly_0 + m_offset;
+}
+// the same with the straight-line square root (lane-pair integrator)
+template <class V>
+__device__ __forceinline__ double valve_mass_flow_fast(double p_in, double p_out, double u, double m_offset, bool& bad) {
+  const double dp = 10.0 * sqrt_inrange(fabs(p_in - p_out), bad) * sgn(p_in - p_out);
   const double u2 = u * u, u3 = u2 * u;
   const double poly_dp = V::c(0) * u3 + V::c(1) * u2 + V::c(2) * u + V::c(3);
   const double poly_0 = V::c(4) * u3 + V::c(5) * u2 + V::c(6) * u + V::c(7);
@@ -98,14 +140,25 @@ __device__ __forceinline__ void compressor_derivative(const double x[5], const d
   dxdt[4] = kTauR * (m_rec_ss - mr);
 }
 
-// Same with the inlet mass flow given (used by the lane-pair integrator).
+// Same with the inlet mass flow given (used by the lane-pair integrator).  FAST: straight-line square
+// roots and division that flag out-of-range operands in `bad` instead of handling them.
+template <bool FAST>
 __device__ __forceinline__ void compressor_derivative_core(const double x[5], const double u[4], double m_in,
-                                                           double p_out, double dxdt[5], double* m_out) {
+                                                           double p_out, double dxdt[5], double* m_out, bool& bad) {
   const double p1 = x[0], p2 = x[1], mc = x[2], wc = x[3], mr = x[4];
-  const double td = u[0] * kTorqueDriveC / wc;
-  *m_out = valve_mass_flow<ValveD>(p2, p_out, u[2], kMoutC);
-  const double m_rec_ss =
-      (u[3] > 1e-2) ? (kMrec0 * (sqrt(p2 * 1e5 - p1 * 1e5) * u[3]) + kMrec1) : 0.0;
+  const double td = FAST ? div_inrange(u[0] * kTorqueDriveC, wc, bad) : u[0] * kTorqueDriveC / wc;
+  *m_out = FAST ? valve_mass_flow_fast<ValveD>(p2, p_out, u[2], kMoutC, bad) : valve_mass_flow<ValveD>(p2, p_out, u[2], kMoutC);
+  double m_rec_ss = 0.0;
+  if (FAST) {
+    // the root is only used with the recycle valve open: an out-of-range operand behind a closed valve is no fault
+    bool bad_r = false;
+    const double rt = sqrt_inrange(p2 * 1e5 - p1 * 1e5, bad_r);
+    const bool open = u[3] > 1e-2;
+    bad |= open && bad_r;
+    m_rec_ss = open ? (kMrec0 * (rt * u[3]) + kMrec1) : 0.0;
+  } else {
+    m_rec_ss = (u[3] > 1e-2) ? (kMrec0 * (sqrt(p2 * 1e5 - p1 * 1e5) * u[3]) + kMrec1) : 0.0;
+  }
   const double mc2 = mc * mc, mc3 = mc * mc2, wc2 = wc * wc;
   const double q2 = map_a(0) * mc3 + map_a(1) * mc2 + map_a(2) * mc + map_a(3);
   const double q1 = map_a(4) * mc3 + map_a(5) * mc2 + map_a(6) * mc + map_a(7);
@@ -351,18 +404,21 @@ __device__ void plant_linearize_part_x(int part, const double* x, const double* 
 // Two neighbouring lanes (parity c = lane & 1) integrate one scenario: lane parity c holds
 // compressor c's five states in xs[0..4]; for the parallel plant both also hold the tank pressure
 // in xs[5] and compute its (identical) derivative.  uc = that compressor's four inputs, u_tank =
-// tank valve (parallel plant).  `full` is the shuffle mask: the two lanes of the pair (pairs of
-// one warp may diverge in the adaptive step loop), or the whole warp when all lanes run in step.
-template <int PLANT>
-__device__ __forceinline__ void pair_derivative(unsigned full, int c, const double xs[6], const double uc[4],
-                                                double u_tank, double d[6]) {
+// tank valve (parallel plant).  All 32 lanes of the warp must call it together (the exchange inside
+// the pair is a whole-warp shuffle; see dopri5_try_step_pair for why).
+template <int PLANT, bool FAST>
+__device__ __forceinline__ void pair_derivative_impl(int c, const double xs[6], const double uc[4],
+                                                     double u_tank, double d[6], bool& bad) {
+  constexpr unsigned full = 0xffffffffu;
   if (PLANT == 0) {
-    const double m_in = valve_mass_flow<ValveC>(1.0, xs[0], uc[1], kMinC);
+    const double m_in = FAST ? valve_mass_flow_fast<ValveC>(1.0, xs[0], uc[1], kMinC, bad)
+                             : valve_mass_flow<ValveC>(1.0, xs[0], uc[1], kMinC);
     double m_out;
-    compressor_derivative_core(xs, uc, m_in, xs[5], d, &m_out);
+    compressor_derivative_core<FAST>(xs, uc, m_in, xs[5], d, &m_out, bad);
     const double m_other = __shfl_xor_sync(full, m_out, 1);
     const double m0 = c == 0 ? m_out : m_other, m1 = c == 0 ? m_other : m_out;
-    const double m_out_tank = valve_mass_flow<ValveD>(xs[5], 1.0, u_tank, kMoutC);
+    const double m_out_tank = FAST ? valve_mass_flow_fast<ValveD>(xs[5], 1.0, u_tank, kMoutC, bad)
+                                   : valve_mass_flow<ValveD>(xs[5], 1.0, u_tank, kMoutC);
     d[5] = (340.0 * 340.0) / kTankVolume * ((m0 + m1) - m_out_tank) * 1e-5;
   } else {
     // serial: compressor 0 discharges into compressor 1's inlet volume
@@ -371,16 +427,40 @@ __device__ __forceinline__ void pair_derivative(unsigned full, int c, const doub
     const double o_uout = __shfl_xor_sync(full, uc[2], 1); // the other compressor's outlet valve
     double m_in, p_out;
     if (c == 0) {
-      m_in = valve_mass_flow<ValveC>(1.0, xs[0], uc[1], kMinC);
+      m_in = FAST ? valve_mass_flow_fast<ValveC>(1.0, xs[0], uc[1], kMinC, bad) : valve_mass_flow<ValveC>(1.0, xs[0], uc[1], kMinC);
       p_out = o_p1;
     } else {
-      m_in = valve_mass_flow<ValveD>(o_p2, xs[0], o_uout, kMoutC);   // first compressor's outflow
+      m_in = FAST ? valve_mass_flow_fast<ValveD>(o_p2, xs[0], o_uout, kMoutC, bad)
+                  : valve_mass_flow<ValveD>(o_p2, xs[0], o_uout, kMoutC);   // first compressor's outflow
       p_out = 1.0;
     }
     double m_out;
-    compressor_derivative_core(xs, uc, m_in, p_out, d, &m_out);
+    compressor_derivative_core<FAST>(xs, uc, m_in, p_out, d, &m_out, bad);
     d[5] = 0.0;
   }
+}
+// The derivative as the integrator uses it: straight-line arithmetic first; a lane pair with an
+// operand outside the range takes the result of the standard operations instead (computed by the
+// whole warp, used by that pair only, so a scenario's numbers never depend on its neighbours).
+template <int PLANT>
+__device__ __forceinline__ void pair_derivative(int c, const double xs[6], const double uc[4], double u_tank, double d[6]) {
+  bool bad = false;
+#ifdef CMPC_NO_FAST_DERIV
+  pair_derivative_impl<PLANT, false>(c, xs, uc, u_tank, d, bad);
+#else
+  pair_derivative_impl<PLANT, true>(c, xs, uc, u_tank, d, bad);
+  const int bad_other = __shfl_xor_sync(0xffffffffu, int(bad), 1);   // (every lane takes part: no short circuit)
+  const bool pair_bad = bad || bad_other != 0;
+  if (__any_sync(0xffffffffu, pair_bad)) {
+    double ds[6];
+    bool unused = false;
+    pair_derivative_impl<PLANT, false>(c, xs, uc, u_tank, ds, unused);
+    if (pair_bad) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) d[i] = ds[i];
+    }
+  }
+#endif
 }
 
 }  // namespace cmpc

@@ -130,7 +130,7 @@ struct DeviceState {
   int* status;         // [B][NCTRL]
   unsigned* active;    // [B][NCTRL]
   double* objective;   // [B][NCTRL]
-  long long* ticks;    // [B][16] per-phase clock64() stamps (CMPC_PHASE_TIMING builds only)
+  long long* ticks;    // [B][32] per-phase clock64() stamps (CMPC_PHASE_TIMING builds only)
 };
 
 // Programmatic dependent launch: the kernels of a step are launched with programmatic stream
@@ -501,9 +501,18 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 }
 
 #ifdef CMPC_PHASE_TIMING
-#define CMPC_TICK(i) do { if (threadIdx.x == 0) { G.ticks[size_t(blockIdx.x) * 16 + (i)] = clock64() - tick_t0_; } } while (0)
+#define CMPC_TICK(i) do { if (threadIdx.x == 0) { G.ticks[size_t(blockIdx.x) * 32 + (i)] = clock64() - tick_t0_; } } while (0)
 #else
 #define CMPC_TICK(i) do { } while (0)
+#endif
+// the same for the one-wave kernels: slot i of scenario `sc`, relative to t0 (stamped by one lane per scenario)
+#ifdef CMPC_PHASE_TIMING
+#define CMPC_TICK_AT(sc, i, t0) do { G.ticks[size_t(sc) * 32 + (i)] = clock64() - (t0); } while (0)
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define CMPC_GTIME_AT(sc, i) do { G.ticks[size_t(sc) * 32 + (i)] = gtime_ns(); } while (0)
+#else
+#define CMPC_TICK_AT(sc, i, t0) do { } while (0)
+#define CMPC_GTIME_AT(sc, i) do { } while (0)
 #endif
 
 // ---- K1: discretisation, prediction and QP assembly of one scenario per CTA --------------------
@@ -514,7 +523,13 @@ template <class S, int RPT, int PCT>
 __global__ void __launch_bounds__(S::NCTRL * S::TPC, assemble_min_blocks(PCT))
 assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
+#ifdef CMPC_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < P.batch) CMPC_GTIME_AT(blockIdx.x, 16);
+#endif
   pdl_wait();
+#ifdef CMPC_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < P.batch) CMPC_GTIME_AT(blockIdx.x, 17);
+#endif
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
   constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NSC = S::NSC, NH = S::NH;
 #ifdef CMPC_PHASE_TIMING
@@ -1189,6 +1204,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     wk[kWBF + N + t] = BF[t * kNC + 0];
     wk[kWBF + 2 * N + t] = BF[t * kNC + 2];
   }
+#ifdef CMPC_PHASE_TIMING
+  if (threadIdx.x == 0) CMPC_GTIME_AT(blockIdx.x, 18);
+#endif
 }
 
 // General solve for one 4-variable QP when the warm-start working set is no longer optimal.
@@ -1259,6 +1277,9 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
   if constexpr (NV == 4 && NCTRL == 2) {
     const int scen = tid >> 1, c = tid & 1;
     if (scen >= P.batch) return;
+#ifdef CMPC_PHASE_TIMING
+    const long long tk0_ = clock64();
+#endif
     const unsigned pm = 3u << (threadIdx.x & 30);   // the two lanes of this scenario
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen) * 2 + c;
@@ -1306,6 +1327,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     unsigned wset = G.guess[rec];
     if (MODE == 1 && it_begin > 0) wset = unsigned(__double_as_longlong(plan[kWPlanSet - kWPlan]));
     if (wset == kQpNoGuess) wset = 0;     // no warm start: begin from the unconstrained minimiser
+    if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 10, tk0_ + (Hm[0][0] != Hm[0][0] ? 1 : 0));   // loads have arrived
     const bool pd = qt_inverse(J);
     QtReduced red;
     bool red_ok = false, need_prep = true;   // red belongs to wset once prepared
@@ -1368,6 +1390,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
 #pragma unroll
       for (int k = 0; k < 4; ++k) z[k] = (status == 0) ? x[k] : 0.0;   // mpc_qp_solver.cc:66-69: zeros on failure
     }
+    if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 11, tk0_ + (z[0] != z[0] ? 1 : 0));   // sweeps done
     // report of the last sweep: active constraints (strictly positive multiplier), objective
     double fmax = 1.0, obj = 0.0;
 #pragma unroll
@@ -1405,6 +1428,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
       // each controller sees only its own inputs move (nerve_center.h:322-328)
       const double du[4] = {z[0], z[1], 0.0, 0.0};
       apriori_update<S>(P, G, rec, du);
+      if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 12, tk0_);
     }
   } else {
     // centralised controller: a single controller has no plan to exchange, every sweep solves the
@@ -1481,9 +1505,20 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
 template <class S>
 __global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
 solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
+#ifdef CMPC_PHASE_TIMING
+  const int sc_ = (blockIdx.x * blockDim.x + threadIdx.x) / S::NCTRL;
+  const bool st_ = (threadIdx.x & 31) == 0 && sc_ < P.batch;
+  if (st_) CMPC_GTIME_AT(sc_, 19);
+#endif
   pdl_wait();
   pdl_trigger();   // single wave
+#ifdef CMPC_PHASE_TIMING
+  if (st_) CMPC_GTIME_AT(sc_, 20);
+#endif
   solve_body<S, 0>(P, G, u, 0, 0);
+#ifdef CMPC_PHASE_TIMING
+  if (st_) CMPC_GTIME_AT(sc_, 21);
+#endif
 }
 
 // The same in pieces, for the timing window only.

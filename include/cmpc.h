@@ -189,8 +189,9 @@ int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* re
  * assemble kernels alone, and resets the counters. */
 int cmpc_set_timing(cmpc_handle* h, int on);
 int cmpc_get_timing(cmpc_handle* h, int64_t* n_steps, double* step_ms, double* assemble_ms);
-/* Developer aid: per-scenario clock64() stamps of the control-step phases of the last launch
- * (B x 16 int64; only filled by builds with -DCMPC_PHASE_TIMING, zeros otherwise). */
+/* Developer aid: per-scenario stamps of the last closed-loop record (B x 32 int64; only filled by builds
+ * with -DCMPC_PHASE_TIMING, zeros otherwise): slots 0-15 clock64() phase stamps inside the kernels, slots
+ * 16-31 %globaltimer (ns) stamps of the kernels' starts and ends (tools/ticks.py names them). */
 int cmpc_debug_phase_ticks(cmpc_handle* h, long long* out);
 /* Number of kernel launches issued by this handle so far (for bench accounting). */
 int cmpc_launch_count(cmpc_handle* h, int64_t* n_launches);

@@ -4,7 +4,7 @@
 import csv, io, subprocess, sys
 rep, kid = sys.argv[1], sys.argv[2]
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", f":::{kid}"],
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", *(["--kernel-id", f":::{kid}"] if kid.isdigit() else ["--kernel-name", f"regex:{kid}"])],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 cur, H, items = None, None, []

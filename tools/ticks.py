@@ -8,7 +8,7 @@ B, T = 4096, 30
 x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
 nc = pkg.from_setup(s, batch=B)
 nc.run_closed_loop(x0, be, bo, T, want_traj=False, want_qp=False)
-ticks = np.zeros((B, 16), dtype=np.int64)
+ticks = np.zeros((B, 32), dtype=np.int64)
 pkg.capi.check(pkg.capi.lib().cmpc_debug_phase_ticks(nc._h, pkg.capi.ptr(ticks)))
 names=["load","rk4","powers","E-gemm","scan","conv","gram","reduce+store"]
 tt=ticks[:, :8]
@@ -16,3 +16,20 @@ dd=np.diff(np.concatenate([np.zeros((B,1),dtype=np.int64), tt], axis=1), axis=1)
 for n_,v,m in zip(names, dd.mean(0), np.median(dd,0)): print(f"  {n_:14s} mean {v:9.0f} median {m:9.0f}")
 print("stages0-2", (ticks[:,9]-ticks[:,1]).mean(), "horner", (ticks[:,8]-ticks[:,9]).mean(), "stages3+", (ticks[:,2]-ticks[:,8]).mean())
 print("total", tt[:,-1].mean(), " | powers: up to end of Horner (stage 4 start):", (ticks[:,8]-ticks[:,0]).mean())
+
+acc = ticks[:, 14] >> 40
+t14 = ticks[:, 14] & ((1 << 40) - 1)
+print("solve_kernel  (cycles from its own start, lane 0 of each scenario): loads arrived %.0f, sweeps done %.0f, end %.0f" % (ticks[:,10].mean(), ticks[:,11].mean(), ticks[:,12].mean()))
+print("integrator: stage 0 starts %.0f, stage 1 starts %.0f, stage 2 starts %.0f, stages done %.0f, error norm done %.0f" % tuple(ticks[:, i].mean() for i in (25, 26, 27, 28, 29)))
+print("advance_kernel: loads arrived %.0f, integration done %.0f, linearisation stored %.0f; accepted steps: %s" % (ticks[:,13].mean(), t14.mean(), ticks[:,15].mean(), np.bincount(acc.astype(int)).tolist()))
+
+g = ticks[:, 16:].astype(np.float64)
+def mm(col, f):
+    v = g[:, col - 16]; v = v[v > 0]
+    return f(v)
+t0 = mm(17, np.min)
+ev = [("K1 first CTA resident", mm(16, np.min)), ("K1 first CTA past its wait", t0), ("K1 last CTA resident", mm(16, np.max)), ("K1 last CTA done", mm(18, np.max)),
+      ("K2 first warp resident", mm(19, np.min)), ("K2 last warp resident", mm(19, np.max)), ("K2 first warp past its wait", mm(20, np.min)), ("K2 last warp past its wait", mm(20, np.max)), ("K2 last warp done", mm(21, np.max)),
+      ("K3 first block resident", mm(22, np.min)), ("K3 first block past its wait", mm(23, np.min)), ("K3 last block past its wait", mm(23, np.max)), ("K3 last block done", mm(24, np.max))]
+print("timeline of the last record (us after the first assemble CTA passed its wait; %globaltimer):")
+for n_, v in ev: print(f"  {n_:30s} {(v - t0) / 1e3:8.2f}")
