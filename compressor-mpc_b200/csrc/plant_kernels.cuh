@@ -432,7 +432,8 @@ __device__ __forceinline__ void advance_post(int b, int c, bool valid, int k, do
 // waves (the 65 536-scenario sweep: 14 waves) are bound by how many integrations an SM holds at once.
 template <class S, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, ClosedLoopArrays A, bool lin_next) {
+cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, ClosedLoopArrays A, bool lin_next,
+                  bool apriori_here) {
   constexpr int kScen = 16, kItems = kScen * S::NCTRL * 3;
   static_assert(kItems <= 96, "one linearisation item per lane of warps 1-3");
   __shared__ double y_sh[kScen][4];
@@ -473,7 +474,7 @@ cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, Clo
       for (int i = 0; i < 4; ++i) y_sh[lane >> 1][i] = y[i];
     }
   } else if (early && item) {
-    lin_part_early<S>(P, G, b0 + sl, g, part, pend);
+    lin_part_early<S>(P, G, b0 + sl, g, part, pend, apriori_here);
   }
   if (!lin_next) return;
   __syncthreads();   // the measurements are in y_sh; with `early`, every part has read the old observer state

@@ -81,7 +81,7 @@ int launch_init(cmpc_handle* h, const double* x, const double* u, const double* 
 }
 
 template <class S>
-int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
+int launch_step_impl(cmpc_handle* h, const double* y, double* u, cudaStream_t st, bool defer_apriori) {
   const int B = h->cfg.batch;
   cudaEvent_t* ev = nullptr;
   if (h->timing) {
@@ -122,7 +122,11 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
     solve_finish_kernel<S><<<solve_grid, 64, 0, st>>>(h->P, h->G, u);
     h->launches++;
   } else {
-    CU(launch_pdl(solve_kernel<S>, solve_grid, 64, 0, st, h->P, h->G, u));
+    // defer_apriori: the plant kernel of the closed loop does UpdateU / ObserveAPriori (lin_part_early)
+    if (defer_apriori)
+      CU(launch_pdl(solve_kernel<S, false>, solve_grid, 64, 0, st, h->P, h->G, u));
+    else
+      CU(launch_pdl(solve_kernel<S, true>, solve_grid, 64, 0, st, h->P, h->G, u));
     if (h->window_on) {   // the window is the whole step: the two inner events coincide
       CU(cudaEventRecord(h->win_ev[h->win_used + 1], st));
       CU(cudaEventRecord(h->win_ev[h->win_used + 2], st));
@@ -133,6 +137,11 @@ int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
   h->launches += 2;
   CU(cudaGetLastError());
   return CMPC_OK;
+}
+
+template <class S>
+int launch_step(cmpc_handle* h, const double* y, double* u, cudaStream_t st) {
+  return launch_step_impl<S>(h, y, u, st, false);
 }
 
 template <class S>
@@ -152,7 +161,10 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
   for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;  // the reference driver accumulates t += Ts
   for (int k = first_step; k < first_step + n_steps; ++k) {
     if (h->window_on) CU(cudaEventRecord(h->win_ev[h->win_used], st));
-    int rc = launch_step<S>(h, A.y, A.u, st);
+    // with the reference's observer gain the plant kernel linearises early and takes the a-priori update
+    // along (the timing window keeps the whole controller step inside its own launches)
+    const bool k3_apriori = h->P.obs_states_free && !(h->window_on && h->window_n >= 0 && h->window_n < h->P.n_iter);
+    int rc = launch_step_impl<S>(h, A.y, A.u, st, k3_apriori);
     if (rc) return rc;
     if (h->window_on) {
       CU(cudaEventRecord(h->win_ev[h->win_used + 3], st));
@@ -160,9 +172,9 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
     }
     // plant side of record k, and the observer update + linearisation of record k + 1
     if (B >= kAdvanceBigBatch)
-      CU(launch_pdl(cl_advance_kernel<S, CMPC_ADV_BIG_MINB>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
+      CU(launch_pdl(cl_advance_kernel<S, CMPC_ADV_BIG_MINB>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true, k3_apriori));
     else
-      CU(launch_pdl(cl_advance_kernel<S, 1>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true));
+      CU(launch_pdl(cl_advance_kernel<S, 1>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true, k3_apriori));
     h->lin_ahead = true;
     h->launches++;
     t += h->cfg.Ts;

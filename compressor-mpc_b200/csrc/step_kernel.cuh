@@ -424,16 +424,44 @@ struct ObsPending {
 
 template <class S>
 __device__ __forceinline__ void lin_part_early(const StepParams& P, const DeviceState& G, int scen, int g, int part,
-                                               ObsPending<S>& pend) {
-  constexpr int N = S::N, NOBS = S::NOBS, NIN = S::NIN;
-  const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
+                                               ObsPending<S>& pend, bool apriori) {
+  constexpr int N = S::N, NOBS = S::NOBS, NIN = S::NIN, NU = S::NU;
+  double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   const double* ss = G.scen + size_t(scen) * kScenStateStride;
   double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
   double xh[N], dx[NOBS];
 #pragma unroll
   for (int i = 0; i < N; ++i) xh[i] = gs[kOffXhat + i];
 #pragma unroll
-  for (int i = 0; i < NOBS; ++i) dx[i] = gs[kOffDx + i];
+  for (int i = N; i < NOBS; ++i) dx[i] = gs[kOffDx + i];
+  if (apriori) {
+    // UpdateU / ObserveAPriori of the record just solved (distributed_controller.h:146-152,
+    // observer.cc:6-19), left to this kernel by solve_kernel<S, false>: same expressions as
+    // apriori_update.  Every part forms the predicted state part it linearises around; part 0 also
+    // moves the delay lines (ring_pos has already been advanced by the host for the next record).
+    const double* wb = wk + kWBF;
+    double du[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) du[k] = (k < NU) ? ss[4 + g * 4 + k] : 0.0;   // first move of the plan (du_old_)
+#pragma unroll
+    for (int i = 0; i < N; ++i) dx[i] = fma(wb[N + i], du[0], fma(wb[2 * N + i], du[2], wb[i]));
+    if (part == 0) {
+      double uold[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) uold[i] = gs[kOffUold + i];
+      const int ring0 = kOffDx + NOBS + 2 + (P.ring_pos + kRing - 1) % kRing, ring1 = ring0 + kRing;
+      const double old0 = gs[ring0], old1 = gs[ring1];
+      gs[kOffDx + NOBS + 0] = old0;
+      gs[kOffDx + NOBS + 1] = old1;
+      gs[ring0] = uold[1] + du[1];
+      gs[ring1] = uold[3] + du[3];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gs[kOffUold + i] = uold[i] + du[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dx[i] = gs[kOffDx + i];
+  }
   if (part == 0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -1269,22 +1297,27 @@ __device__ __forceinline__ void apriori_update(const StepParams& P, const Device
 // out of the measured time): MODE 1 runs sweeps [it_begin, it_end) and parks plan, working set and
 // status in the hand-over record; MODE 2 is what follows the sweeps (first move, UpdateU /
 // ObserveAPriori).  Sweeps 0..n-1 followed by n..n_iter-1 and MODE 2 leave exactly the state MODE 0 does.
-template <class S, int MODE>
+// APRIORI = false leaves UpdateU / ObserveAPriori to the plant kernel that follows in the closed loop
+// (lin_part_early), where the lanes that linearise the next record have time to spare.
+template <class S, int MODE, bool APRIORI = true>
 __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceState& G, double* __restrict__ u,
                                            int it_begin, int it_end) {
   constexpr int NU = S::NU, NV = S::NV, NVO = S::NVO, NCTRL = S::NCTRL;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (NV == 4 && NCTRL == 2) {
-    const int scen = tid >> 1, c = tid & 1;
-    if (scen >= P.batch) return;
+    // Lanes past the end of the batch work along on its last scenario and store nothing: the plan
+    // exchange below is a whole-warp shuffle (one mask per lane pair would send it through
+    // WARPSYNC.COLLECTIVE, group by group, in every sweep), so the warp must stay whole.
+    const bool valid = (tid >> 1) < P.batch;
+    const int scen = valid ? (tid >> 1) : P.batch - 1, c = tid & 1;
 #ifdef CMPC_PHASE_TIMING
     const long long tk0_ = clock64();
 #endif
-    const unsigned pm = 3u << (threadIdx.x & 30);   // the two lanes of this scenario
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen) * 2 + c;
     double* plan = G.work + rec * kWorkStride + kWPlan;
     if constexpr (MODE == 2) {
+      if (!valid) return;
       double zf[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) zf[k] = plan[k];
@@ -1303,15 +1336,14 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     const double* gf = G.qpf + rec * 4;
     const double* gG = G.qpG + rec * 16;
     const double* uo = G.ctrl + rec * kCtrlStateStride + kOffUold;
-    double J[4][4], Hm[4][4], Gx[4][4], f0[4], z[4], bnd[16];
+    double J[4][4], Gx[4][4], f0[4], z[4], bnd[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       f0[i] = gf[i];
       z[i] = (MODE == 1 && it_begin > 0) ? plan[i] : ss[4 + c * 4 + i];   // du_prev = du_old_ (own plan)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        Hm[i][j] = gH[i * 4 + j];
-        J[i][j] = Hm[i][j];
+        J[i][j] = gH[i * 4 + j];
         Gx[i][j] = gG[i * 4 + j];
       }
     }
@@ -1327,7 +1359,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     unsigned wset = G.guess[rec];
     if (MODE == 1 && it_begin > 0) wset = unsigned(__double_as_longlong(plan[kWPlanSet - kWPlan]));
     if (wset == kQpNoGuess) wset = 0;     // no warm start: begin from the unconstrained minimiser
-    if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 10, tk0_ + (Hm[0][0] != Hm[0][0] ? 1 : 0));   // loads have arrived
+    if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 10, tk0_ + (J[0][0] != J[0][0] ? 1 : 0));   // loads have arrived
     const bool pd = qt_inverse(J);
     QtReduced red;
     bool red_ok = false, need_prep = true;   // red belongs to wset once prepared
@@ -1337,7 +1369,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     for (int it = it_lo; it < it_hi; ++it) {
       double zo[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) zo[k] = __shfl_xor_sync(pm, z[k], 1);   // the other controller's previous plan
+      for (int k = 0; k < 4; ++k) zo[k] = __shfl_xor_sync(0xffffffffu, z[k], 1);   // the other controller's previous plan
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double s = f0[i];
@@ -1390,6 +1422,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
 #pragma unroll
       for (int k = 0; k < 4; ++k) z[k] = (status == 0) ? x[k] : 0.0;   // mpc_qp_solver.cc:66-69: zeros on failure
     }
+    if (!valid) return;   // (after the last shuffle)
     if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 11, tk0_ + (z[0] != z[0] ? 1 : 0));   // sweeps done
     // report of the last sweep: active constraints (strictly positive multiplier), objective
     double fmax = 1.0, obj = 0.0;
@@ -1398,7 +1431,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
       fmax = fmax > fabs(fi[i]) ? fmax : fabs(fi[i]);
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s = fma(Hm[i][k], z[k], s);
+      for (int k = 0; k < 4; ++k) s = fma(gH[i * 4 + k], z[k], s);   // (re-read: H is not kept through the sweeps)
       obj += z[i] * (0.5 * s + fi[i]);
     }
     unsigned act = 0, m = wset & 0xffffu;
@@ -1427,7 +1460,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
       u[size_t(scen) * 4 + 2 * c + 1] = un1;
       // each controller sees only its own inputs move (nerve_center.h:322-328)
       const double du[4] = {z[0], z[1], 0.0, 0.0};
-      apriori_update<S>(P, G, rec, du);
+      if (APRIORI) apriori_update<S>(P, G, rec, du);
       if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 12, tk0_);
     }
   } else {
@@ -1497,12 +1530,12 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
         ss[k] = un;
         u[size_t(scen) * 4 + k] = un;
       }
-      apriori_update<S>(P, G, rec, du);
+      if (APRIORI) apriori_update<S>(P, G, rec, du);
     }
   }
 }
 
-template <class S>
+template <class S, bool APRIORI>
 __global__ void __launch_bounds__(64, CMPC_SOLVE_MIN_BLOCKS)
 solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
 #ifdef CMPC_PHASE_TIMING
@@ -1515,7 +1548,7 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
 #ifdef CMPC_PHASE_TIMING
   if (st_) CMPC_GTIME_AT(sc_, 20);
 #endif
-  solve_body<S, 0>(P, G, u, 0, 0);
+  solve_body<S, 0, APRIORI>(P, G, u, 0, 0);
 #ifdef CMPC_PHASE_TIMING
   if (st_) CMPC_GTIME_AT(sc_, 21);
 #endif
