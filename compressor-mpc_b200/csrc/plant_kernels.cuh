@@ -197,17 +197,17 @@ __device__ __forceinline__ bool dopri5_try_step_pair(bool go, int c, const doubl
     }
   }
 #endif
-  double sumsq = 0.0;
+  // sum in plant state order (compressor 0's states, compressor 1's, tank), as the one-thread form does:
+  // lane 0 of the pair sums its five, lane 1 continues from there and hands the total back
+  double part = e2[0];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {   // compressor 0's states
-    const double o = __shfl_xor_sync(0xffffffffu, e2[i], 1);
-    sumsq += (c == 0) ? e2[i] : o;
-  }
+  for (int i = 1; i < 5; ++i) part += e2[i];
+  const double first = __shfl_xor_sync(0xffffffffu, part, 1);   // (lane 1 receives compressor 0's sum)
+  double tot = first;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {   // compressor 1's states
-    const double o = __shfl_xor_sync(0xffffffffu, e2[i], 1);
-    sumsq += (c == 1) ? e2[i] : o;
-  }
+  for (int i = 0; i < 5; ++i) tot += e2[i];
+  const double both = __shfl_xor_sync(0xffffffffu, tot, 1);      // (lane 0 receives the sum of all ten)
+  double sumsq = (c == 0) ? both : tot;
   if (PLANT == 0) sumsq += e2[5];
 #ifdef CMPC_NO_FAST_ERR
   double err = sqrt(sumsq);

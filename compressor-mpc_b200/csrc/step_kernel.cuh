@@ -1310,9 +1310,6 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     // WARPSYNC.COLLECTIVE, group by group, in every sweep), so the warp must stay whole.
     const bool valid = (tid >> 1) < P.batch;
     const int scen = valid ? (tid >> 1) : P.batch - 1, c = tid & 1;
-#ifdef CMPC_PHASE_TIMING
-    const long long tk0_ = clock64();
-#endif
     double* ss = G.scen + size_t(scen) * kScenStateStride;
     const size_t rec = size_t(scen) * 2 + c;
     double* plan = G.work + rec * kWorkStride + kWPlan;
@@ -1337,16 +1334,12 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     const double* gG = G.qpG + rec * 16;
     const double* uo = G.ctrl + rec * kCtrlStateStride + kOffUold;
     double J[4][4], Gx[4][4], f0[4], z[4], bnd[16];
+    // What the assemble kernel of this record does not write (own previous plan, applied inputs, warm
+    // start: all left by the previous record's solve kernel) is fetched BEFORE the dependent-launch wait
+    // of the production kernel, together with the first touch of the parameter block.
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f0[i] = gf[i];
+    for (int i = 0; i < 4; ++i)
       z[i] = (MODE == 1 && it_begin > 0) ? plan[i] : ss[4 + c * 4 + i];   // du_prev = du_old_ (own plan)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        J[i][j] = gH[i * 4 + j];
-        Gx[i][j] = gG[i * 4 + j];
-      }
-    }
     const double uo0 = uo[0], uo1 = uo[1];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1359,8 +1352,29 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     unsigned wset = G.guess[rec];
     if (MODE == 1 && it_begin > 0) wset = unsigned(__double_as_longlong(plan[kWPlanSet - kWPlan]));
     if (wset == kQpNoGuess) wset = 0;     // no warm start: begin from the unconstrained minimiser
+    const double us0 = ss[2 * c], us1 = ss[2 * c + 1];   // NerveCenter's u_old_ of this controller's inputs
+    if constexpr (MODE == 0) {
+      pdl_wait();
+      pdl_trigger();   // single wave
+#ifdef CMPC_PHASE_TIMING
+      if (c == 0) CMPC_GTIME_AT(scen, 20);
+#endif
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f0[i] = gf[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        J[i][j] = gH[i * 4 + j];
+        Gx[i][j] = gG[i * 4 + j];
+      }
+    }
+#ifdef CMPC_PHASE_TIMING
+    const long long tk0_ = clock64();
+#endif
     if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 10, tk0_ + (J[0][0] != J[0][0] ? 1 : 0));   // loads have arrived
     const bool pd = qt_inverse(J);
+    if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 30, tk0_ + (J[0][0] != J[0][0] ? 1 : 0));   // inverse done
     QtReduced red;
     bool red_ok = false, need_prep = true;   // red belongs to wset once prepared
     double x[4] = {0.0, 0.0, 0.0, 0.0}, lam[4] = {0.0, 0.0, 0.0, 0.0}, fi[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1421,6 +1435,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) z[k] = (status == 0) ? x[k] : 0.0;   // mpc_qp_solver.cc:66-69: zeros on failure
+      if (c == 0 && MODE == 0 && it == 0) CMPC_TICK_AT(scen, 31, tk0_ + (z[0] != z[0] ? 1 : 0));   // first sweep done
     }
     if (!valid) return;   // (after the last shuffle)
     if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 11, tk0_ + (z[0] != z[0] ? 1 : 0));   // sweeps done
@@ -1453,7 +1468,7 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
       // du_old_ = du_prev; u_old_ += first move of each controller's plan (system order = ctrl 0, ctrl 1)
 #pragma unroll
       for (int k = 0; k < 4; ++k) ss[4 + c * 4 + k] = z[k];
-      const double un0 = ss[2 * c] + z[0], un1 = ss[2 * c + 1] + z[1];
+      const double un0 = us0 + z[0], un1 = us1 + z[1];
       ss[2 * c] = un0;
       ss[2 * c + 1] = un1;
       u[size_t(scen) * 4 + 2 * c] = un0;
@@ -1467,6 +1482,10 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     // centralised controller: a single controller has no plan to exchange, every sweep solves the
     // same QP (distributed_controller.h:215-218), so one solve gives the result of all sweeps
     static_assert(NVO == 0 && NCTRL == 1, "generic path is the centralised controller");
+    if constexpr (MODE == 0) {
+      pdl_wait();
+      pdl_trigger();   // single wave
+    }
     const int scen = tid;
     if (scen >= P.batch) return;
     double* ss = G.scen + size_t(scen) * kScenStateStride;
@@ -1543,12 +1562,7 @@ solve_kernel(StepParams P, DeviceState G, double* __restrict__ u) {
   const bool st_ = (threadIdx.x & 31) == 0 && sc_ < P.batch;
   if (st_) CMPC_GTIME_AT(sc_, 19);
 #endif
-  pdl_wait();
-  pdl_trigger();   // single wave
-#ifdef CMPC_PHASE_TIMING
-  if (st_) CMPC_GTIME_AT(sc_, 20);
-#endif
-  solve_body<S, 0, APRIORI>(P, G, u, 0, 0);
+  solve_body<S, 0, APRIORI>(P, G, u, 0, 0);   // (waits for the assemble kernel inside, after its own preparations)
 #ifdef CMPC_PHASE_TIMING
   if (st_) CMPC_GTIME_AT(sc_, 21);
 #endif
