@@ -661,6 +661,7 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
   A.block_end = block_end_dev; A.block_off = block_off_dev; A.n_blocks = n_blocks;
   A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
   A.qp_status = qp_status_dev; A.n_steps = total_steps; A.rec_base = 0;
+  A.stream_io = 0;
   const int rc = h->ops->closed_loop(h, first_step, n_steps, x0_dev, A, reinit,
                                                    static_cast<cudaStream_t>(stream));
   h->stream_next = -1;   // a cmpc_closed_loop_start / _step sequence does not survive a run of this kind
@@ -703,18 +704,36 @@ int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* re
     return fail(CMPC_ERR_STATE, "the controller was restarted since cmpc_closed_loop_start");
   const size_t B = h->cfg.batch, REC = 1 + h->N + 8;
   const int k = h->stream_next;
-  CU(cudaMemcpyAsync(h->d_step_off, plant_offset, B * h->NIN * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // Page-locked host buffers that are mapped into the device (cudaHostAlloc / cudaHostRegister, e.g. pinned
+  // torch tensors) are read and written by the plant kernel itself, in contiguous chunks, while the solve
+  // kernel runs / the plant is integrated: no copy sits in front of the control step or behind the plant
+  // advance.  Anything else goes through the handle's device buffers and two copies on the stream.
+  auto mapped = [&](const void* host, size_t align) -> void* {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return (reinterpret_cast<uintptr_t>(at.devicePointer) % align == 0) ? at.devicePointer : nullptr;
+  };
+  const bool no_direct = h->generic || getenv("CMPC_NO_DIRECT_HOST_IO") != nullptr;   // (the env variable: A/B measurements)
+  const double* off_dev = no_direct ? nullptr : static_cast<const double*>(mapped(plant_offset, 8));
+  double* rec_dev = no_direct ? nullptr : static_cast<double*>(mapped(record, 16));
+  const bool rec_direct = rec_dev != nullptr;
+  if (!off_dev) {
+    CU(cudaMemcpyAsync(h->d_step_off, plant_offset, B * h->NIN * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    off_dev = h->d_step_off;
+  }
   ClosedLoopArrays A;
   A.x = h->d_x; A.y = h->d_y; A.u = h->d_u; A.ring = h->d_ring;
-  A.block_end = h->d_step_end; A.block_off = h->d_step_off; A.n_blocks = 1;
-  A.traj = h->d_rec; A.qp_active = nullptr; A.qp_objective = nullptr; A.qp_status = nullptr;
+  A.block_end = h->d_step_end; A.block_off = off_dev; A.n_blocks = 1;
+  A.traj = rec_direct ? rec_dev : h->d_rec; A.qp_active = nullptr; A.qp_objective = nullptr; A.qp_status = nullptr;
   A.n_steps = 1; A.rec_base = k;
+  A.stream_io = h->generic ? 0 : 1;
   if (int rc = h->ops->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) {
     h->stream_next = -1;
     h->loop_started = false;
     return rc;
   }
-  CU(cudaMemcpyAsync(record, h->d_rec, B * REC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (!rec_direct) CU(cudaMemcpyAsync(record, h->d_rec, B * REC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->stream_next = k + 1;
   h->loop_next = k + 1;

@@ -283,6 +283,9 @@ struct ClosedLoopArrays {
   int* qp_status;
   int n_steps;         // records per scenario in traj / qp_* ...
   int rec_base;        // ... whose slot 0 is record rec_base of the run
+  int stream_io;       // 1: one record per launch with n_blocks == 1 (cmpc_closed_loop_step): block_off and traj may be
+                       // page-locked HOST memory mapped into the device, so a block moves its scenarios' offsets and
+                       // record rows through shared memory as whole 16-byte pieces of contiguous chunks
 };
 
 // Start of a closed-loop run: x = x0, y = GetOutput(x0), rings = 0.
@@ -327,7 +330,7 @@ struct AdvancePre {
 // the warp stays whole, and stores nothing)
 template <int PLANT>
 __device__ __forceinline__ void advance_pre(int b, int c, bool valid, int k, double t_k, const ClosedLoopArrays& A,
-                                            AdvancePre<PLANT>& S) {
+                                            AdvancePre<PLANT>& S, const double* off_sh, double* rec_sh) {
   constexpr int N = PlantDims<PLANT>::N, NIN = PlantDims<PLANT>::NIN, REC = 1 + N + 8;
 #pragma unroll
   for (int i = 0; i < 5; ++i) S.xs[i] = A.x[size_t(b) * N + 5 * c + i];
@@ -335,19 +338,20 @@ __device__ __forceinline__ void advance_pre(int b, int c, bool valid, int k, dou
   // plant-input offsets of the block this record belongs to (SetOffset); TimeDelay: this
   // compressor's recycle valve command (control input 2c+1) comes out 40 samples late
   int blk = 0;
-  while (blk + 1 < A.n_blocks && k >= A.block_end[b * A.n_blocks + blk]) ++blk;
+  if (!off_sh)
+    while (blk + 1 < A.n_blocks && k >= A.block_end[b * A.n_blocks + blk]) ++blk;
   S.ring_slot = A.ring + (size_t(b) * 2 + c) * kDelay + k % kDelay;
   S.ud = *S.ring_slot;
   constexpr double udef_par[9] = {0.304, 0.43, 1.0, 0, 0.304, 0.43, 1.0, 0, 0.7};
   constexpr double udef_ser[8] = {0.304, 0.405, 1, 0, 0.304, -1, 0.393, 0};
-  const double* off = A.block_off + (size_t(b) * A.n_blocks + blk) * NIN;
+  const double* off = off_sh ? off_sh : A.block_off + (size_t(b) * A.n_blocks + blk) * NIN;   // (off_sh: this scenario's row)
 #pragma unroll
   for (int i = 0; i < 4; ++i) S.uc[i] = (PLANT == 0 ? udef_par[4 * c + i] : udef_ser[4 * c + i]) + off[4 * c + i];
   S.uc[3] += S.ud;
   S.u_tank = PLANT == 0 ? udef_par[8] + off[PLANT == 0 ? 8 : 0] : 0.0;
   S.rec = nullptr;
   if (A.traj && valid) {
-    double* r = A.traj + (size_t(b) * A.n_steps + (k - A.rec_base)) * REC;
+    double* r = rec_sh ? rec_sh : A.traj + (size_t(b) * A.n_steps + (k - A.rec_base)) * REC;   // (rec_sh: this scenario's row)
     S.rec = r;
 #pragma unroll
     for (int i = 0; i < 5; ++i) r[1 + 5 * c + i] = S.xs[i];
@@ -366,6 +370,7 @@ __device__ __forceinline__ void advance_post(int b, int c, bool valid, int k, do
                                              const ClosedLoopArrays& A, const int* __restrict__ status,
                                              const unsigned* __restrict__ active,
                                              const double* __restrict__ objective, double (&y_next)[4], double* ks,
+                                             const double* rec_sh, double* rec_out, int rec_len,
                                              long long* tick_out = nullptr, long long tick_t0 = 0) {
   constexpr int N = PlantDims<PLANT>::N;
   double u[4];
@@ -378,6 +383,15 @@ __device__ __forceinline__ void advance_post(int b, int c, bool valid, int k, do
   if (S.rec && c == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) S.rec[1 + N + i] = u[i];
+  }
+  if (rec_sh && rec_out) {
+    // the block's record rows are complete in shared memory: out they go as one contiguous chunk, 16 bytes
+    // per lane and store (whole sectors, so the chunk may be mapped host memory), while the plant is integrated
+    __syncwarp();
+    const double2* src = reinterpret_cast<const double2*>(rec_sh);
+    double2* dst = reinterpret_cast<double2*>(rec_out);
+    for (int i = threadIdx.x & 31; i < rec_len / 2; i += 32) dst[i] = src[i];
+    if ((rec_len & 1) && (threadIdx.x & 31) == 0) rec_out[rec_len - 1] = rec_sh[rec_len - 1];   // (ragged last block of an odd-length record)
   }
   if (c < NCTRL && valid) {
     const size_t o = (size_t(b) * A.n_steps + (k - A.rec_base)) * NCTRL + c;
@@ -448,7 +462,18 @@ cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, Clo
   AdvancePre<S::PLANT> pre;
   const bool valid = b0 + (lane >> 1) < P.batch;            // warp 0: this lane pair has a scenario
   const int b = valid ? b0 + (lane >> 1) : P.batch - 1, c = lane & 1;
-  if (warp == 0) advance_pre<S::PLANT>(b, c, valid, k, t_k, A, pre);
+  constexpr int NIN = S::NIN, REC = 1 + S::N + 8;
+  __shared__ __align__(16) double off_sh[kScen * NIN];
+  __shared__ __align__(16) double rec_sh[kScen * REC];
+  const int n_here = P.batch - b0 < kScen ? P.batch - b0 : kScen;   // scenarios of this block
+  if (A.stream_io) {
+    // this block's plant-input offsets: one contiguous chunk (possibly of mapped host memory), read once
+    for (int i = threadIdx.x; i < n_here * NIN; i += blockDim.x) off_sh[i] = A.block_off[size_t(b0) * NIN + i];
+    __syncthreads();
+  }
+  if (warp == 0)
+    advance_pre<S::PLANT>(b, c, valid, k, t_k, A, pre, A.stream_io ? off_sh + (b - b0) * NIN : nullptr,
+                          A.stream_io ? rec_sh + (b - b0) * REC : nullptr);
   pdl_wait();
   pdl_trigger();   // single wave
 #ifdef CMPC_PHASE_TIMING
@@ -465,9 +490,11 @@ cl_advance_kernel(StepParams P, DeviceState G, int k, double t_k, double Ts, Clo
     double y[4];
 #ifdef CMPC_PHASE_TIMING
     advance_post<S::PLANT, S::NCTRL>(b, c, valid, k, Ts, pre, A, G.status, G.active, G.objective, y, ks_sh + lane,
+                                     A.stream_io ? rec_sh : nullptr, A.traj ? A.traj + size_t(b0) * REC : nullptr, n_here * REC,
                                      G.ticks + size_t(b) * 32, tk0_);
 #else
-    advance_post<S::PLANT, S::NCTRL>(b, c, valid, k, Ts, pre, A, G.status, G.active, G.objective, y, ks_sh + lane);
+    advance_post<S::PLANT, S::NCTRL>(b, c, valid, k, Ts, pre, A, G.status, G.active, G.objective, y, ks_sh + lane,
+                                     A.stream_io ? rec_sh : nullptr, A.traj ? A.traj + size_t(b0) * REC : nullptr, n_here * REC);
 #endif
     if (c == 0 && valid) {
 #pragma unroll

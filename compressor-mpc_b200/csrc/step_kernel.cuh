@@ -226,8 +226,24 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 // operands live zero-padded to K = 12 in shared memory (the pads are exact zeros: planted with the
 // seeds and reproduced by every product, see the load phase of assemble_kernel), so the loads need
 // no predicates; rows or columns beyond the 12 only feed output rows/columns that are never stored.
+// Which row of its 8-row block a lane holds (A fragment and result alike) is ours to choose, as long as
+// the A loads and the use of the result agree: lanes 4i..4i+3 take row frag_row = i with its two low
+// bits swapped (0 2 1 3 4 6 5 7).  A quarter warp -- the unit in which 16-byte accesses are served --
+// then stores rows r and r + 2 of a result tile instead of r and r + 1, which with the row strides used
+// here (12, 20, 68, ... doubles: 6, 10, 34 sixteen-byte slots, i.e. 6 or 2 modulo the 8 slots of a
+// wavefront) touch 8 different slots: the tile stores lose their two-way bank conflicts (5 % of the kernel's
+// shared-memory wavefronts).  The 8-byte fragment loads see the same four rows per half warp as before.
+// Measured: assemble_kernel -0.4 % at p = 100, -1.4 % at p = 200 (tools/ab.sh, -DCMPC_FRAG_ROW_IDENTITY).
+__device__ __forceinline__ int frag_row(int lane) {
+  const int r = lane >> 2;
+#ifdef CMPC_FRAG_ROW_IDENTITY   // (A/B builds)
+  return r;
+#else
+  return (r & 4) | ((r & 1) << 1) | ((r >> 1) & 1);
+#endif
+}
 __device__ __forceinline__ void frag_a(const double* A, int lda, int mt, int lane, double (&a)[3]) {
-  const double* p = A + (8 * mt + (lane >> 2)) * lda + (lane & 3);
+  const double* p = A + (8 * mt + frag_row(lane)) * lda + (lane & 3);
   a[0] = p[0];
   a[1] = p[4];
   a[2] = p[8];
@@ -322,7 +338,7 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[W], int lane
 template <bool ADD_EYE = false>
 __device__ __forceinline__ void tile_store(double* C, int ldc, int row_off, int col_off, int mc, int nc_pad,
                                            int mt, int nt, int lane, const double (&c)[2], int n_eye = 0) {
-  const int r = 8 * mt + (lane >> 2), cc = 8 * nt + 2 * (lane & 3);
+  const int r = 8 * mt + frag_row(lane), cc = 8 * nt + 2 * (lane & 3);
   if (r < mc && cc < nc_pad) {
     double2 v;
     v.x = c[0];
@@ -859,7 +875,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
       tile_store(Pn, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cq[0]);
       if constexpr (v_merged) {
-        const int r = 8 * mt_w + (lane >> 2), q = lane & 3;
+        const int r = 8 * mt_w + frag_row(lane), q = lane & 3;
         if (r < kLD) {
           double2 v;
           v.x = cq[1][0];
@@ -907,7 +923,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
           tile_store(R, ldr, 0, r_base * kNC, kLD, f_cols, mt_w, k - sq_tiles, lane, ct);
         } else {
           // the pruned part may start at an odd column: 8-byte stores
-          const int r = 8 * mt_w + (lane >> 2), m = 8 * (k - sq_tiles - f_tiles) + 2 * (lane & 3);
+          const int r = 8 * mt_w + frag_row(lane), m = 8 * (k - sq_tiles - f_tiles) + 2 * (lane & 3);
           if (r < kLD) {
             if (m < p_cols) R[r * ldr + p_col0 + m] = ct[0];
             if (m + 1 < p_cols) R[r * ldr + p_col0 + m + 1] = ct[1];
@@ -951,7 +967,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     // row block mt of L is output mt, its rows are the baby steps a: a lane's two results are
     // channels (cc, cc + 1) of row a + 8 b (cc is even, so both stay inside block b)
     auto store_e = [&](int mt, int nt, const double (&c)[2]) {
-      const int a = lane >> 2, n = 8 * nt + 2 * (lane & 3);
+      const int a = frag_row(lane), n = 8 * nt + 2 * (lane & 3);
       if (n < kNC * b_full) {
         const int b = n / kNC, cc = n % kNC;
         double* e = E + (mt * kNC + cc) * ldE + kBaby * b + a;
@@ -974,7 +990,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
 #pragma unroll
       for (int mt = 0; mt < NY; ++mt) {
         const double (&cz)[2] = czz[mt];
-        const int a = lane >> 2, y = mt, n = 2 * (lane & 3);
+        const int a = frag_row(lane), y = mt, n = 2 * (lane & 3);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int r = 8 * (n + e) + a - 1;

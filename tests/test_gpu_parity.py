@@ -804,6 +804,31 @@ def test_streaming_closed_loop_with_host_buffers(setups, pkg, gpu_lib):
         assert np.array_equal(rec, ref[:, k]), k
 
 
+@pytest.mark.parametrize("case,B", [("coop-par", 37), ("cent-ser", 16), ("ncoop-ser", 5)])
+def test_streaming_closed_loop_with_page_locked_buffers(setups, pkg, gpu_lib, case, B):
+    """The same with page-locked (mapped) host buffers: the plant kernel reads the offsets and writes the
+    record rows itself, chunk by chunk (no copies on the stream).  Ragged last block, both plants; a
+    buffer that is only 8-byte aligned goes back to the copy path.  Bit for bit in every case."""
+    import torch
+    s = setups[case]
+    x_def, _ = ol.plant_defaults(s.plant)
+    n, T = len(x_def), 50
+    x0, be, bo = pkg.scenarios.make_scenarios(s, x_def, B, T)
+    be[:, 0] = 15 + np.arange(B) % 20
+    ref = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)["traj"]
+    nc = pkg.from_setup(s, batch=B)
+    nc.closed_loop_start(x0)
+    off = torch.empty((B, bo.shape[2]), dtype=torch.float64).pin_memory()
+    big = torch.empty((B * (1 + n + 8) + 1,), dtype=torch.float64).pin_memory()
+    rec_al, rec_odd = big[:-1].view(B, 1 + n + 8), big[1:].view(B, 1 + n + 8)   # 16-byte aligned / not
+    for k in range(T):
+        off.copy_(torch.from_numpy(np.stack([bo[b, min(int((k >= be[b]).sum()), be.shape[1] - 1)] for b in range(B)])))
+        rec = rec_al if k % 3 else rec_odd
+        rec.fill_(float("nan"))
+        nc.closed_loop_step_raw(off.data_ptr(), rec.data_ptr())
+        assert np.array_equal(rec.numpy(), ref[:, k]), k
+
+
 def test_argument_validation_added_in_round_two(setups, pkg, gpu_lib):
     import torch
     s = setups["coop-par"]

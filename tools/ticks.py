@@ -33,3 +33,28 @@ ev = [("K1 first CTA resident", mm(16, np.min)), ("K1 first CTA past its wait", 
       ("K3 first block resident", mm(22, np.min)), ("K3 first block past its wait", mm(23, np.min)), ("K3 last block past its wait", mm(23, np.max)), ("K3 last block done", mm(24, np.max))]
 print("timeline of the last record (us after the first assemble CTA passed its wait; %globaltimer):")
 for n_, v in ev: print(f"  {n_:30s} {(v - t0) / 1e3:8.2f}")
+
+tot = tt[:, -1].astype(np.float64)
+print("per-scenario assemble time (cycles): p5 %.0f p50 %.0f p95 %.0f max %.0f" % tuple(np.percentile(tot, [5, 50, 95, 100])))
+import os
+W = int(os.environ.get("CMPC_TICKS_WAVE", "592"))
+cta = np.arange(B) % W
+per_cta = np.bincount(cta, weights=tot, minlength=W)
+print("per-CTA sum over its scenarios (persistent grid of %d): min %.0f mean %.0f max %.0f cycles = %.1f / %.1f / %.1f us" % (W, per_cta.min(), per_cta.mean(), per_cta.max(), per_cta.min()/1965, per_cta.mean()/1965, per_cta.max()/1965))
+rnd = np.arange(B) // W
+for r in range(rnd.max() + 1): print("  round %d: mean %.0f max %.0f" % (r, tot[rnd == r].mean(), tot[rnd == r].max()))
+e18 = g[:, 18 - 16]
+print("assemble CTA end times (us after start): p5 %.1f p50 %.1f p95 %.1f max %.1f (last round only)" % tuple((np.percentile(e18[rnd == rnd.max()], [5, 50, 95, 100]) - t0) / 1e3))
+
+if os.environ.get("CMPC_TICKS_SMID"):
+    smid = ticks[:, 19]
+    sms = np.unique(smid)
+    m = np.array([tot[smid == k].mean() for k in sms]); n = np.array([(smid == k).sum() for k in sms])
+    o = np.argsort(m)
+    print("SMs seen", len(sms), " scenarios per SM: min %d max %d" % (n.min(), n.max()))
+    print("per-SM mean scenario time, fastest 10:", [(int(sms[i]), int(m[i]), int(n[i])) for i in o[:10]])
+    print("slowest 10:", [(int(sms[i]), int(m[i]), int(n[i])) for i in o[-10:]])
+    print("by smid parity: even %.0f odd %.0f" % (m[sms % 2 == 0].mean(), m[sms % 2 == 1].mean()))
+    for lo in range(0, 160, 16): 
+        sel = (sms >= lo) & (sms < lo + 16)
+        if sel.any(): print("  smid %3d..%3d: mean %.0f  scenarios %d" % (lo, lo + 15, m[sel].mean(), n[sel].sum()))
