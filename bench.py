@@ -484,6 +484,26 @@ def main():
             e2e_s += time.perf_counter() - t0
             e2e_mismatch = max(e2e_mismatch, float((rec_host - ref_traj[:, k]).abs().max()))
     e2e_value = world * B * K / D.reduce(e2e_s, "max")
+    # the same loop pipelined (cmpc_closed_loop_pipeline: the control step of record k + 1 is launched behind the
+    # plant advance of record k and runs while the host handles record k), W + K calls back to back under one
+    # clock: the calls overlap by design, so there is no place for an L2 flush between them -- reported next to
+    # `e2e`, not instead of it
+    nc.closed_loop_start(x0)
+    nc.closed_loop_pipeline(True)
+    pipe_mismatch = 0.0
+    for k in range(W):
+        nc.closed_loop_step_raw(off_ptrs[k], rec_ptr)
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        nc.closed_loop_step_raw(off_ptrs[k], rec_ptr)
+    torch.cuda.synchronize()
+    pipe_s = time.perf_counter() - t0
+    pipe_mismatch = float((rec_host - ref_traj[:, W + K - 1]).abs().max())
+    e2e_pipe_value = world * B * K / D.reduce(pipe_s, "max")
+    nc.closed_loop_start(x0)
+    nc.closed_loop_pipeline(False)
 
     # the control step alone through the reference-facing call (cmpc_get_next_input: host y -> host u),
     # replaying the measurements of the device run
@@ -596,6 +616,10 @@ def main():
                     "api": "cmpc_closed_loop_step (pinned host plant-input offsets -> control step + plant advance "
                            "on the device -> pinned host record [t, x, u, y]), blocking",
                     "max_abs_diff_vs_device_run": e2e_mismatch},
+            "e2e_pipelined": {"value": e2e_pipe_value, "unit": UNIT, "h2d_bytes_per_step": B * nin * 8, "d2h_bytes_per_step": B * rec * 8,
+                              "api": "cmpc_closed_loop_pipeline(1) + cmpc_closed_loop_step, all calls back to back under one clock "
+                                     "(no L2 flush: consecutive calls overlap by design)",
+                              "max_abs_diff_vs_device_run_last_record": pipe_mismatch},
             "e2e_control_step": {"value": ctl_value, "unit": UNIT, "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": B * 32,
                                  "api": "cmpc_get_next_input (host y -> host u, pinned): the control step alone, "
                                         "as the reference's ControllerInterface::GetNextInput", "max_abs_du_vs_device_run": max_du},

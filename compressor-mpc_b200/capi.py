@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "cmpc_last_error", "cmpc_set_weights", "cmpc_set_output_reference", "cmpc_set_constraints",
     "cmpc_set_observer_gain", "cmpc_initialize", "cmpc_get_next_input",
     "cmpc_get_next_input_device", "cmpc_get_next_input_timed", "cmpc_run_closed_loop_timed", "cmpc_get_step_info", "cmpc_run_closed_loop",
-    "cmpc_run_closed_loop_device", "cmpc_closed_loop_start", "cmpc_closed_loop_step", "cmpc_launch_count", "cmpc_set_capture", "cmpc_set_timing",
+    "cmpc_run_closed_loop_device", "cmpc_closed_loop_start", "cmpc_closed_loop_step", "cmpc_closed_loop_pipeline", "cmpc_launch_count", "cmpc_set_capture", "cmpc_set_timing",
     "cmpc_get_timing", "cmpc_debug_phase_ticks",
     "cmpc_get_linearization", "cmpc_get_qp", "cmpc_generate_prediction",
     "cmpc_get_controller_state", "cmpc_solve_qp", "cmpc_plant_eval", "cmpc_plant_integrate",

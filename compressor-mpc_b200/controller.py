@@ -230,6 +230,11 @@ class NerveCenter:
         x0 = f64(np.broadcast_to(f64(x0), (self.batch, self.n_states)))
         check(lib().cmpc_closed_loop_start(self._h, ptr(x0)))
 
+    def closed_loop_pipeline(self, on: bool = True):
+        """Before the first step of a streaming run: launch the control step of the next record behind each
+        plant advance, so that it runs while the caller handles the record (cmpc_closed_loop_pipeline)."""
+        check(lib().cmpc_closed_loop_pipeline(self._h, 1 if on else 0))
+
     def closed_loop_step(self, plant_offset) -> np.ndarray:
         """One sample: plant-input offsets (B, n_inputs) in, record [t, x, u, y] (B, 1+n+8) out."""
         off = f64(np.broadcast_to(f64(plant_offset), (self.batch, self.n_inputs)))

@@ -419,6 +419,7 @@ int cmpc_destroy(cmpc_handle* h) {
                   h->d_step_end, h->d_step_off, h->d_rec};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->ev_plant) cudaEventDestroy(h->ev_plant);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->win_ev) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -662,6 +663,7 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
   A.traj = traj_dev; A.qp_active = qp_active_dev; A.qp_objective = qp_objective_dev;
   A.qp_status = qp_status_dev; A.n_steps = total_steps; A.rec_base = 0;
   A.stream_io = 0;
+  A.phases = 3;
   const int rc = h->ops->closed_loop(h, first_step, n_steps, x0_dev, A, reinit,
                                                    static_cast<cudaStream_t>(stream));
   h->stream_next = -1;   // a cmpc_closed_loop_start / _step sequence does not survive a run of this kind
@@ -693,6 +695,16 @@ int cmpc_closed_loop_start(cmpc_handle* h, const double* x0) {
   }
   h->stream_next = 0;
   h->loop_started = false;
+  h->ctrl_ahead = false;
+  return CMPC_OK;
+}
+
+int cmpc_closed_loop_pipeline(cmpc_handle* h, int on) {
+  CMPC_ENTER(h);
+  if (h->stream_next > 0) return fail(CMPC_ERR_STATE, "the pipelining of a closed loop is chosen before its first step");
+  if (on && h->generic) return fail(CMPC_ERR_UNSUPPORTED, "general configurations run the closed loop unpipelined");
+  if (on && !h->ev_plant) CU(cudaEventCreateWithFlags(&h->ev_plant, cudaEventDisableTiming));
+  h->stream_pipeline = on != 0;
   return CMPC_OK;
 }
 
@@ -728,13 +740,36 @@ int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* re
   A.traj = rec_direct ? rec_dev : h->d_rec; A.qp_active = nullptr; A.qp_objective = nullptr; A.qp_status = nullptr;
   A.n_steps = 1; A.rec_base = k;
   A.stream_io = h->generic ? 0 : 1;
-  if (int rc = h->ops->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) {
+  A.phases = 3;
+  auto give_up = [&](int rc) {
     h->stream_next = -1;
     h->loop_started = false;
+    h->ctrl_ahead = false;
     return rc;
+  };
+  if (!h->stream_pipeline) {
+    if (int rc = h->ops->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) return give_up(rc);
+    if (!rec_direct) CU(cudaMemcpyAsync(record, h->d_rec, B * REC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  } else {
+    // Pipelined (cmpc_closed_loop_pipeline): a control step needs the measurement, not the plant-input offsets
+    // of its record, so the control step of record k + 1 is launched right behind the plant advance of record k
+    // and runs while the caller looks at record k and prepares the next offsets; this call then only adds the
+    // plant advance and waits for it.
+    if (!h->ctrl_ahead) {
+      A.phases = 1;
+      if (int rc = h->ops->closed_loop(h, k, 1, h->d_xinit, A, k == 0, h->stream)) return give_up(rc);
+    }
+    A.phases = 2;
+    if (int rc = h->ops->closed_loop(h, k, 1, h->d_xinit, A, false, h->stream)) return give_up(rc);
+    if (!rec_direct) CU(cudaMemcpyAsync(record, h->d_rec, B * REC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev_plant, h->stream));
+    A.phases = 1;
+    A.rec_base = k + 1;
+    if (int rc = h->ops->closed_loop(h, k + 1, 1, h->d_xinit, A, false, h->stream)) return give_up(rc);
+    h->ctrl_ahead = true;
+    CU(cudaEventSynchronize(h->ev_plant));
   }
-  if (!rec_direct) CU(cudaMemcpyAsync(record, h->d_rec, B * REC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
   h->stream_next = k + 1;
   h->loop_next = k + 1;
   h->loop_total = -1;   // not a run the device-resident variant could continue

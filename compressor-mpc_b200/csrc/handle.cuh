@@ -99,6 +99,9 @@ struct cmpc_handle {
   // closed loop one record per call with host I/O (cmpc_closed_loop_start / _step)
   int* d_step_end = nullptr;
   double *d_step_off = nullptr, *d_rec = nullptr;
+  bool stream_pipeline = false;   // cmpc_closed_loop_pipeline: the control step of the next record is launched ahead
+  bool ctrl_ahead = false;        // ... and has been for record stream_next
+  cudaEvent_t ev_plant = nullptr; // end of the plant advance of the record being returned
   int stream_next = -1;
   size_t smem_bytes = 0;
   int64_t launches = 0;

@@ -283,6 +283,7 @@ struct ClosedLoopArrays {
   int* qp_status;
   int n_steps;         // records per scenario in traj / qp_* ...
   int rec_base;        // ... whose slot 0 is record rec_base of the run
+  int phases;          // launch_closed_loop: bit 0 the control step of each record, bit 1 its plant advance (3: both)
   int stream_io;       // 1: one record per launch with n_blocks == 1 (cmpc_closed_loop_step): block_off and traj may be
                        // page-locked HOST memory mapped into the device, so a block moves its scenarios' offsets and
                        // record rows through shared memory as whole 16-byte pieces of contiguous chunks

@@ -160,23 +160,27 @@ int launch_closed_loop(cmpc_handle* h, int first_step, int n_steps, const double
   double t = 0.0;
   for (int k = 0; k < first_step; ++k) t += h->cfg.Ts;  // the reference driver accumulates t += Ts
   for (int k = first_step; k < first_step + n_steps; ++k) {
-    if (h->window_on) CU(cudaEventRecord(h->win_ev[h->win_used], st));
     // with the reference's observer gain the plant kernel linearises early and takes the a-priori update
     // along (the timing window keeps the whole controller step inside its own launches)
     const bool k3_apriori = h->P.obs_states_free && !(h->window_on && h->window_n >= 0 && h->window_n < h->P.n_iter);
-    int rc = launch_step_impl<S>(h, A.y, A.u, st, k3_apriori);
-    if (rc) return rc;
-    if (h->window_on) {
-      CU(cudaEventRecord(h->win_ev[h->win_used + 3], st));
-      h->win_used += 4;
+    if (A.phases & 1) {
+      if (h->window_on) CU(cudaEventRecord(h->win_ev[h->win_used], st));
+      int rc = launch_step_impl<S>(h, A.y, A.u, st, k3_apriori);
+      if (rc) return rc;
+      if (h->window_on) {
+        CU(cudaEventRecord(h->win_ev[h->win_used + 3], st));
+        h->win_used += 4;
+      }
     }
     // plant side of record k, and the observer update + linearisation of record k + 1
-    if (B >= kAdvanceBigBatch)
-      CU(launch_pdl(cl_advance_kernel<S, CMPC_ADV_BIG_MINB>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true, k3_apriori));
-    else
-      CU(launch_pdl(cl_advance_kernel<S, 1>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true, k3_apriori));
-    h->lin_ahead = true;
-    h->launches++;
+    if (A.phases & 2) {
+      if (B >= kAdvanceBigBatch)
+        CU(launch_pdl(cl_advance_kernel<S, CMPC_ADV_BIG_MINB>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true, k3_apriori));
+      else
+        CU(launch_pdl(cl_advance_kernel<S, 1>, (B + 15) / 16, 128, 0, st, h->P, h->G, k, t, h->cfg.Ts, A, true, k3_apriori));
+      h->lin_ahead = true;
+      h->launches++;
+    }
     t += h->cfg.Ts;
   }
   CU(cudaGetLastError());

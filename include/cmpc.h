@@ -179,8 +179,17 @@ int cmpc_run_closed_loop_device(cmpc_handle* h, int first_step, int n_steps, int
  * places scenario b at x0[b] (B x n_states) with the controller initialised like the reference
  * driver; every cmpc_closed_loop_step uploads this sample's plant-input offsets (B x n_inputs,
  * added to the default input), runs the control step and the plant advance on the device and
- * downloads the record [t, x, u, y] (B x (1+n_states+8)).  Blocking; runs on the handle's stream. */
+ * downloads the record [t, x, u, y] (B x (1+n_states+8)).  Blocking; runs on the handle's stream.
+ * Buffers that are page-locked and mapped into the device (cudaHostAlloc / cudaHostRegister, pinned torch
+ * tensors; the record 16-byte aligned) are read and written by the plant kernel itself, in contiguous
+ * chunks, with no copy on the stream; any other host memory goes through two copies.
+ * cmpc_closed_loop_pipeline(h, 1), called before the first step of a run, lets every step launch the control
+ * step of the NEXT record behind its plant advance (a control step needs the measurement the plant advance
+ * produces, not the next plant-input offsets), so that it runs while the caller consumes the record and
+ * prepares the next call; records are identical either way.  While pipelined, the read-back hooks
+ * (cmpc_get_step_info, cmpc_get_qp, ...) show the record that has been launched ahead. */
 int cmpc_closed_loop_start(cmpc_handle* h, const double* x0);
+int cmpc_closed_loop_pipeline(cmpc_handle* h, int on);
 int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* record);
 /* Per-kernel device timing: when on, every control step (linearise [host-facing step only],
  * assemble, solve) is bracketed by CUDA events on its stream (which also keeps its kernels from

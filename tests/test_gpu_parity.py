@@ -804,8 +804,9 @@ def test_streaming_closed_loop_with_host_buffers(setups, pkg, gpu_lib):
         assert np.array_equal(rec, ref[:, k]), k
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
 @pytest.mark.parametrize("case,B", [("coop-par", 37), ("cent-ser", 16), ("ncoop-ser", 5)])
-def test_streaming_closed_loop_with_page_locked_buffers(setups, pkg, gpu_lib, case, B):
+def test_streaming_closed_loop_with_page_locked_buffers(setups, pkg, gpu_lib, case, B, pipelined):
     """The same with page-locked (mapped) host buffers: the plant kernel reads the offsets and writes the
     record rows itself, chunk by chunk (no copies on the stream).  Ragged last block, both plants; a
     buffer that is only 8-byte aligned goes back to the copy path.  Bit for bit in every case."""
@@ -818,6 +819,7 @@ def test_streaming_closed_loop_with_page_locked_buffers(setups, pkg, gpu_lib, ca
     ref = pkg.from_setup(s, batch=B).run_closed_loop(x0, be, bo, T)["traj"]
     nc = pkg.from_setup(s, batch=B)
     nc.closed_loop_start(x0)
+    nc.closed_loop_pipeline(pipelined)   # (the control step of the next record launched ahead, or not)
     off = torch.empty((B, bo.shape[2]), dtype=torch.float64).pin_memory()
     big = torch.empty((B * (1 + n + 8) + 1,), dtype=torch.float64).pin_memory()
     rec_al, rec_odd = big[:-1].view(B, 1 + n + 8), big[1:].view(B, 1 + n + 8)   # 16-byte aligned / not
@@ -827,6 +829,13 @@ def test_streaming_closed_loop_with_page_locked_buffers(setups, pkg, gpu_lib, ca
         rec.fill_(float("nan"))
         nc.closed_loop_step_raw(off.data_ptr(), rec.data_ptr())
         assert np.array_equal(rec.numpy(), ref[:, k]), k
+    if pipelined:
+        with pytest.raises(pkg.capi.CmpcError, match="before its first step"):
+            nc.closed_loop_pipeline(False)
+        # a restart drops the control step that was launched ahead
+        nc.closed_loop_start(x0)
+        nc.closed_loop_step_raw(off.data_ptr(), rec_al.data_ptr())
+        assert np.array_equal(rec_al.numpy()[:, :1 + n], ref[:, 0, :1 + n])
 
 
 def test_argument_validation_added_in_round_two(setups, pkg, gpu_lib):

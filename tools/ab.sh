@@ -17,7 +17,7 @@ except Exception as e:
     print(v, rep, "no result", e); raise SystemExit
 r, s = d["roofline"], d["sweep"]
 print(f"{v:10s} #{rep} value {d['value']/1e6:6.2f} M  ms/step {d['ms_per_step']*1e3:6.1f} us  b2b {d['value_back_to_back']/1e6:6.2f} M  "
-      f"asm {r['kernel_ms']*1e3:6.1f} us ({r['frac']:.3f})  ctrl {r['control_step_ms']*1e3:6.1f} us  e2e {d['e2e']['value']/1e6:5.2f} M  "
+      f"asm {r['kernel_ms']*1e3:6.1f} us ({r['frac']:.3f})  ctrl {r['control_step_ms']*1e3:6.1f} us  e2e {d['e2e']['value']/1e6:5.2f} M (pipelined {d.get('e2e_pipelined',{}).get('value',0)/1e6:5.2f} M)  "
       f"ctl-e2e {d['e2e_control_step']['value']/1e6:5.2f} M | sweep {s['value']/1e6:6.2f} M asm {s['roofline']['kernel_ms']*1e3:7.1f} us "
       f"({s['roofline']['frac']:.3f}) parity {d['health']['gpu_vs_oracle_max_rel_err_u']:.1e}/{s['health']['gpu_vs_oracle_max_rel_err_u']:.1e} "
       f"act {d['health']['active_sets_identical']}/{s['health']['active_sets_identical']} fail {d['health']['qp_failures']}+{s['health']['qp_failures']}")
