@@ -19,9 +19,9 @@ print("total", tt[:,-1].mean(), " | powers: up to end of Horner (stage 4 start):
 
 acc = ticks[:, 14] >> 40
 t14 = ticks[:, 14] & ((1 << 40) - 1)
-print("solve_kernel  (cycles from its own start, lane 0 of each scenario): loads arrived %.0f, inverse done %.0f, first sweep done %.0f, sweeps done %.0f, end %.0f" % (ticks[:,10].mean(), ticks[:,30].mean(), ticks[:,31].mean(), ticks[:,11].mean(), ticks[:,12].mean()))
-print("integrator: stage 0 starts %.0f, stage 1 starts %.0f, stage 2 starts %.0f, stages done %.0f, error norm done %.0f" % tuple(ticks[:, i].mean() for i in (25, 26, 27, 28, 29)))
-print("advance_kernel: loads arrived %.0f, integration done %.0f, linearisation stored %.0f; accepted steps: %s" % (ticks[:,13].mean(), t14.mean(), ticks[:,15].mean(), np.bincount(acc.astype(int)).tolist()))
+print("solve_kernel  (cycles after its QP data arrived, lane 0 of each scenario): inverse done %.0f, first sweep done %.0f, sweeps done %.0f, end %.0f" % (ticks[:,30].mean(), ticks[:,31].mean(), ticks[:,11].mean(), ticks[:,12].mean()))
+print("integrator (same clock): stage 0 starts %.0f, stage 1 starts %.0f, stage 2 starts %.0f, stages done %.0f, error norm done %.0f" % tuple(ticks[:, i].mean() for i in (25, 26, 27, 28, 29)))
+print("advance_kernel (cycles after its wait): inputs arrived %.0f, integration done %.0f, linearisation stored %.0f; accepted steps: %s" % (ticks[:,13].mean(), t14.mean(), ticks[:,15].mean(), np.bincount(acc.astype(int)).tolist()))
 
 g = ticks[:, 16:].astype(np.float64)
 def mm(col, f):
