@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "cmpc_last_error", "cmpc_set_weights", "cmpc_set_output_reference", "cmpc_set_constraints",
     "cmpc_set_observer_gain", "cmpc_initialize", "cmpc_get_next_input",
     "cmpc_get_next_input_device", "cmpc_get_next_input_timed", "cmpc_run_closed_loop_timed", "cmpc_get_step_info", "cmpc_run_closed_loop",
-    "cmpc_run_closed_loop_device", "cmpc_closed_loop_start", "cmpc_closed_loop_step", "cmpc_closed_loop_pipeline", "cmpc_launch_count", "cmpc_set_capture", "cmpc_set_timing",
+    "cmpc_run_closed_loop_device", "cmpc_closed_loop_start", "cmpc_closed_loop_step", "cmpc_closed_loop_pipeline", "cmpc_inrange_math", "cmpc_launch_count", "cmpc_set_capture", "cmpc_set_timing",
     "cmpc_get_timing", "cmpc_debug_phase_ticks",
     "cmpc_get_linearization", "cmpc_get_qp", "cmpc_generate_prediction",
     "cmpc_get_controller_state", "cmpc_solve_qp", "cmpc_plant_eval", "cmpc_plant_integrate",
@@ -146,3 +146,13 @@ def plant_integrate(plant, x, u, Ts=0.05, device=0):
     ns = np.zeros(x.shape[0], dtype=np.int32)
     check(lib().cmpc_plant_integrate(device, plant, x.shape[0], ptr(x), ptr(u), C.c_double(Ts), ptr(ns)))
     return x, ns
+
+
+def inrange_math(a, b, device=0):
+    """sqrt(a) and a / b by the plant integrator's straight-line forms and by the standard operations."""
+    a = f64(np.ravel(a)); b = f64(np.ravel(b))
+    n = a.shape[0]
+    out = [np.empty(n) for _ in range(4)]
+    flagged = np.zeros(n, dtype=np.int32)
+    check(lib().cmpc_inrange_math(device, n, ptr(a), ptr(b), *(ptr(o) for o in out), ptr(flagged)))
+    return {"sqrt_fast": out[0], "sqrt_std": out[1], "div_fast": out[2], "div_std": out[3], "flagged": flagged}

@@ -1055,4 +1055,21 @@ int cmpc_plant_integrate(int device, int plant, int nq, double* x, const double*
   return CMPC_OK;
 }
 
+int cmpc_inrange_math(int device, int n, const double* a, const double* b, double* sqrt_fast, double* sqrt_std,
+                      double* div_fast, double* div_std, int32_t* flagged) {
+  if (n <= 0 || !a || !b || !sqrt_fast || !sqrt_std || !div_fast || !div_std || !flagged)
+    return fail(CMPC_ERR_ARG, "bad argument");
+  CMPC_ENTER_DEVICE(device);
+  DevBuf<double> da, db, d1, d2, d3, d4;
+  DevBuf<int> df;
+  CU(da.upload(a, n)); CU(db.upload(b, n));
+  CU(d1.alloc(n)); CU(d2.alloc(n)); CU(d3.alloc(n)); CU(d4.alloc(n)); CU(df.alloc(n));
+  inrange_math_kernel<<<(n + 127) / 128, 128>>>(n, da.p, db.p, d1.p, d2.p, d3.p, d4.p, df.p);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  CU(d1.download(sqrt_fast, n)); CU(d2.download(sqrt_std, n)); CU(d3.download(div_fast, n)); CU(d4.download(div_std, n));
+  CU(df.download(flagged, n));
+  return CMPC_OK;
+}
+
 }  // extern "C"

@@ -588,6 +588,20 @@ __global__ void plant_integrate_kernel(int nq, double* x, const double* __restri
   if (n_substeps && ln == 0) n_substeps[b] = s;
 }
 
+// The straight-line square root and division of the plant integrator next to the standard operations
+// (parity hook: cmpc_inrange_math).
+static __global__ void inrange_math_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* sqrt_fast,
+                                    double* sqrt_std, double* div_fast, double* div_std, int* flagged) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool bad_s = false, bad_d = false;
+  sqrt_fast[i] = sqrt_inrange(a[i], bad_s);
+  sqrt_std[i] = sqrt(a[i]);
+  div_fast[i] = div_inrange(a[i], b[i], bad_d);
+  div_std[i] = a[i] / b[i];
+  flagged[i] = (bad_s ? 1 : 0) | (bad_d ? 2 : 0);
+}
+
 template <int NV>
 __global__ void qp_kernel(int nq, const double* __restrict__ H, const double* __restrict__ f,
                           const double* __restrict__ lb, const double* __restrict__ ub,

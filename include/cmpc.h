@@ -240,6 +240,13 @@ int cmpc_plant_eval(int device, int plant, int nq, const double* x, const double
  * x nq x n in/out, u nq x n_inputs (already offset + delayed).  n_substeps nq (may be NULL). */
 int cmpc_plant_integrate(int device, int plant, int nq, double* x, const double* u, double Ts,
                          int32_t* n_substeps);
+/* The plant integrator's straight-line square root and division (sqrt_inrange / div_inrange in
+ * csrc/plant_dev.cuh: the fast path of the IEEE routines without their branch to the special cases)
+ * next to the standard operations, element by element: sqrt(a[i]) and a[i] / b[i] both ways, and
+ * flagged[i] = 1 if the square root, 2 if the division (3: both) reported an operand outside its range --
+ * the cases in which the integrator redoes its derivative with the standard operations. */
+int cmpc_inrange_math(int device, int n, const double* a, const double* b, double* sqrt_fast, double* sqrt_std,
+                      double* div_fast, double* div_std, int32_t* flagged);
 
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct cmpc_fp64_peak {

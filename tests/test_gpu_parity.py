@@ -58,6 +58,37 @@ def test_plant_integrate_matches_oracle(plant, pkg, gpu_lib):
         assert np.allclose(Xg[b], xo, rtol=1e-10, atol=1e-13)
 
 
+def test_straight_line_sqrt_and_division_round_like_the_standard_ones(pkg, gpu_lib):
+    """The integrator's branch-free square root and division (plant_dev.cuh) against sqrt() and / on the
+    device: identical bits over the magnitudes a plant state can take and far beyond; operands outside
+    [1e-290, 1e290] (zero, negative roots, infinities, NaN) are flagged, which is when the integrator
+    falls back to the standard operations."""
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    a = np.exp(rng.uniform(np.log(1e-280), np.log(1e280), n))
+    a[: n // 4] = rng.uniform(1e-3, 1e3, n // 4)                    # where the plant lives
+    a[n // 4: n // 2] = 1.0 + rng.uniform(-1, 1, n // 4) * 1e-9      # differences of nearly equal pressures
+    b = np.exp(rng.uniform(np.log(1e-140), np.log(1e140), n)) * rng.choice([-1.0, 1.0], n)
+    b[: n // 4] = rng.uniform(0.1, 1e4, n // 4)
+    r = pkg.capi.inrange_math(a, b)
+    ok = r["flagged"] == 0
+    with np.errstate(over="ignore", under="ignore"):
+        q = a / b
+    representable = (np.abs(q) > 1e-290) & (np.abs(q) < 1e290)
+    assert ok[: n // 2].all() and ok.mean() > 0.99
+    assert np.array_equal(r["sqrt_fast"][ok], r["sqrt_std"][ok])
+    assert np.array_equal(r["sqrt_std"], np.sqrt(a))
+    sel = ok & representable
+    d = np.abs(r["div_fast"][sel] - r["div_std"][sel]) / np.abs(r["div_std"][sel])
+    assert d.max() <= 2.3e-16, d.max()                               # at most one unit in the last place ...
+    assert (r["div_fast"][sel] == r["div_std"][sel]).mean() > 0.999   # ... and almost never that
+    edge_a = np.array([0.0, -1.0, np.inf, np.nan, 1e-300, 1e300, 4.0, 1.0, 0.0, 1e-300])
+    edge_b = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0, 1e-300, 2.0, 3.0])
+    e = pkg.capi.inrange_math(edge_a, edge_b)
+    assert (e["flagged"][:6] & 1).all() and (e["flagged"][6:8] & 2).all() and (e["flagged"][9] & 2)
+    assert e["flagged"][8] == 1 and e["div_fast"][8] == 0.0           # 0 / 2: fine for the division (and sqrt(0) is flagged)
+
+
 @pytest.mark.parametrize("nv", [4, 8])
 def test_qp_solver_matches_oracle(nv, pkg, gpu_lib):
     rng = np.random.default_rng(3)
