@@ -109,8 +109,10 @@ def run_reference(args):
     setup = load_setup(pkg, args.case)
     x_def, _ = ol.plant_defaults(setup.plant)
     cores = os.cpu_count() or 1
-    bs = args.ref_scenarios
     W, K = args.warmup, args.steps
+    # a bounded sample of the 4096 scenarios, sized for about 10 s of CPU work (3 k steps/s per thread) whatever K is,
+    # so that thread start-up does not decide the figure
+    bs = min(4096, max(args.ref_scenarios, -(-32768 // max(K, 1))))
     x0, be, bo = pkg.scenarios.make_scenarios(setup, x_def, bs, W + K)
     o = ol.Oracle(setup, p=args.p)
     o.run_closed_loop(x0, be, bo, max(W, 1), n_threads=cores)          # warm-up
@@ -532,7 +534,8 @@ def main():
     cores = os.cpu_count() or 1
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        bs, ks = args.cpu_sample, min(K, 200)
+        ks = min(K, 200)
+        bs = min(B, max(args.cpu_sample, -(-32768 // (W + ks))))   # about 10 s of CPU work (see run_reference)
         dt, parity, act_equal = oracle_sample(pkg, setup, p, x0[:bs], be[:bs], bo[:bs], W + ks, d_traj, d_act, n, cores)
         sys.path.insert(0, str(ROOT / "tests"))
         import oracle_lib as ol

@@ -1391,6 +1391,14 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
     if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 10, tk0_ + (J[0][0] != J[0][0] ? 1 : 0));   // loads have arrived
     const bool pd = qt_inverse(J);
     if (c == 0 && MODE == 0) CMPC_TICK_AT(scen, 30, tk0_ + (J[0][0] != J[0][0] ? 1 : 0));   // inverse done
+    // H^-1 is only needed when a reduced system is built (once per step, and again after a change of the
+    // working set): it waits in shared memory instead of holding 32 registers through the sweeps, where
+    // the reduced system, the cross term and the bounds already fill the register file
+    __shared__ double J_sh[16 * 64];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) J_sh[(i * 4 + j) * 64 + threadIdx.x] = J[i][j];
     QtReduced red;
     bool red_ok = false, need_prep = true;   // red belongs to wset once prepared
     double x[4] = {0.0, 0.0, 0.0, 0.0}, lam[4] = {0.0, 0.0, 0.0, 0.0}, fi[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1417,7 +1425,12 @@ __device__ __forceinline__ void solve_body(const StepParams& P, const DeviceStat
         int n_rep = 0;
         for (;;) {
           if (need_prep) {
-            red_ok = qt_prepare(J, bnd, wset, red);
+            double Jl[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) Jl[i][j] = J_sh[(i * 4 + j) * 64 + threadIdx.x];
+            red_ok = qt_prepare(Jl, bnd, wset, red);
             need_prep = false;
           }
           const bool ok = qt_eval(red, fi, bnd, wset, x, lam) && red_ok;

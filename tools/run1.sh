@@ -1,9 +1,9 @@
-python -m pytest tests/test_gpu_parity.py -x -q -k "page_locked or streaming" 2>&1 | tail -3
-for v in "" 1; do
-  echo "== CMPC_NO_EARLY_RETURN=$v"
-  if [ -n "$v" ]; then export CMPC_NO_EARLY_RETURN=1; fi
-  python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-b1 --no-sweep 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('value %.2f M  ms/step %.1f us  e2e %.2f M (%.1f us/record)  diff vs device run %s' % (d['value']/1e6, d['ms_per_step']*1e3, d['e2e']['value']/1e6, 4096/d['e2e']['value']*1e6, d['e2e'].get('max_abs_diff_vs_device_run')))"
-done
+# scratch: one-off GPU checks (overwritten as needed)
+( time python -c "import __graft_entry__ as g; g.smoke()" ) 2>&1 | tail -4
+( time python bench.py > gpurun_out/r02c/bench_default.json 2> gpurun_out/r02c/bench_default.err ) 2>&1 | tail -3
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/r02c/bench_default.json') if l.startswith('{')][-1])
+print({k:d[k] for k in ('value','steps','warmup','ms_per_step','gpu_launches','n_gpus')}, d['e2e']['value'], d['cpu_baseline']['value'], d['roofline']['frac'])"
+( time python bench.py --impl reference > gpurun_out/r02c/bench_ref_default.json 2>> gpurun_out/r02c/bench_default.err ) 2>&1 | tail -3
+tail -1 gpurun_out/r02c/bench_ref_default.json | cut -c1-300
