@@ -91,6 +91,15 @@ void update_obs_states_free(cmpc_handle* h) {
   h->P.obs_states_free = free_ ? 1 : 0;
 }
 
+// Device address of a host buffer that is page-locked and mapped into the device (cudaHostAlloc /
+// cudaHostRegister, pinned torch tensors) and aligned as asked; null for anything else.
+void* mapped_host(const void* host, size_t align) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return (reinterpret_cast<uintptr_t>(at.devicePointer) % align == 0) ? at.devicePointer : nullptr;
+}
+
 // First statement of every entry point that takes a handle: argument check, then the handle's
 // device becomes current until the entry point returns (DeviceGuard puts the caller's back).
 #define CMPC_ENTER(h)                                                                              \
@@ -582,10 +591,18 @@ int cmpc_get_next_input(cmpc_handle* h, const double* y, double* u) {
   if (h->lin_ahead) return fail(CMPC_ERR_STATE, "a closed-loop run owns the controller state: call cmpc_initialize first");
   if (!y || !u) return fail(CMPC_ERR_ARG, "null argument");
   const size_t bytes = size_t(h->cfg.batch) * 4 * sizeof(double);
-  CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, h->stream));
-  int rc = h->ops->step(h, h->d_y, h->d_u, h->stream);
+  // Page-locked buffers that are mapped into the device are used directly (as in cmpc_closed_loop_step): the
+  // linearisation kernel brings the measurements in, the solve kernel writes the inputs out, and no copy
+  // stands in front of or behind the step.  Anything else goes through the handle's device buffers.
+  const bool no_direct = h->generic || getenv("CMPC_NO_DIRECT_HOST_IO") != nullptr;
+  const double* y_map = no_direct ? nullptr : static_cast<const double*>(mapped_host(y, 8));
+  double* u_map = no_direct ? nullptr : static_cast<double*>(mapped_host(u, 16));
+  if (!y_map) CU(cudaMemcpyAsync(h->d_y, y, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->y_mapped_src = y_map;
+  int rc = h->ops->step(h, h->d_y, u_map ? u_map : h->d_u, h->stream);
+  h->y_mapped_src = nullptr;
   if (rc) return rc;
-  CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (!u_map) CU(cudaMemcpyAsync(u, h->d_u, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return CMPC_OK;
 }
@@ -720,12 +737,7 @@ int cmpc_closed_loop_step(cmpc_handle* h, const double* plant_offset, double* re
   // torch tensors) are read and written by the plant kernel itself, in contiguous chunks, while the solve
   // kernel runs / the plant is integrated: no copy sits in front of the control step or behind the plant
   // advance.  Anything else goes through the handle's device buffers and two copies on the stream.
-  auto mapped = [&](const void* host, size_t align) -> void* {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
-    return (reinterpret_cast<uintptr_t>(at.devicePointer) % align == 0) ? at.devicePointer : nullptr;
-  };
+  auto mapped = [&](const void* host, size_t align) -> void* { return mapped_host(host, align); };
   const bool no_direct = h->generic || getenv("CMPC_NO_DIRECT_HOST_IO") != nullptr;   // (the env variable: A/B measurements)
   const double* off_dev = no_direct ? nullptr : static_cast<const double*>(mapped(plant_offset, 8));
   double* rec_dev = no_direct ? nullptr : static_cast<double*>(mapped(record, 16));

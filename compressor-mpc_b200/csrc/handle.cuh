@@ -99,6 +99,8 @@ struct cmpc_handle {
   // closed loop one record per call with host I/O (cmpc_closed_loop_start / _step)
   int* d_step_end = nullptr;
   double *d_step_off = nullptr, *d_rec = nullptr;
+  const double* y_mapped_src = nullptr;   // cmpc_get_next_input: device address of a mapped host measurement buffer
+                                           // that lin_kernel reads itself (null: y is already on the device)
   bool stream_pipeline = false;   // cmpc_closed_loop_pipeline: the control step of the next record is launched ahead
   bool ctrl_ahead = false;        // ... and has been for record stream_next
   cudaEvent_t ev_plant = nullptr; // end of the plant advance of the record being returned

@@ -98,7 +98,7 @@ int launch_step_impl(cmpc_handle* h, const double* y, double* u, cudaStream_t st
   // the previous record's plant kernel has already done this work (lin_ahead).
   if (!h->lin_ahead) {
     const int n_thr = B * S::NCTRL * 4;
-    CU(launch_pdl(lin_kernel<S>, (n_thr + 127) / 128, 128, 0, st, h->P, h->G, y));
+    CU(launch_pdl(lin_kernel<S>, (n_thr + 127) / 128, 128, 0, st, h->P, h->G, const_cast<double*>(y), h->y_mapped_src));
     h->launches++;
   }
   if (ev) CU(cudaEventRecord(ev[1], st));

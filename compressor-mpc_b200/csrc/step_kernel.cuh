@@ -529,7 +529,7 @@ __device__ __forceinline__ void lin_finish(const StepParams& P, const DeviceStat
 
 template <class S>
 __global__ void __launch_bounds__(128)
-lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
+lin_kernel(StepParams P, DeviceState G, double* __restrict__ y, const double* __restrict__ y_from) {
   pdl_wait();
   pdl_trigger();   // single wave: the next grid may queue up behind it at once
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,6 +537,16 @@ lin_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int scen = quad / S::NCTRL, g = quad % S::NCTRL;
   const bool on = scen < P.batch;
   const unsigned m = __ballot_sync(0xffffffffu, on);
+  if (y_from) {
+    // cmpc_get_next_input with a page-locked measurement buffer: the block brings its scenarios' rows in
+    // itself, one contiguous chunk of mapped host memory read once, and leaves them where the assemble
+    // kernel expects them (instead of a copy on the stream in front of the step)
+    constexpr int kScenPerBlock = 32 / S::NCTRL;
+    const int s0 = blockIdx.x * kScenPerBlock;
+    const int n_here = P.batch - s0 < kScenPerBlock ? P.batch - s0 : kScenPerBlock;
+    if (int(threadIdx.x) < n_here * 4) y[size_t(s0) * 4 + threadIdx.x] = y_from[size_t(s0) * 4 + threadIdx.x];
+    __syncthreads();
+  }
   if (!on) return;
   double yv[4];
 #pragma unroll

@@ -111,7 +111,8 @@ int cmpc_initialize(cmpc_handle* h, const double* x_init, const double* u_init,
 
 /* ControllerInterface::GetNextInput / NerveCenter::GetNextInputWithTiming
  * (controller_interface.h:46, nerve_center.h:125-182), batched: y B x 4 -> u B x 4.
- * Host buffers; H2D of y and D2H of u happen inside.
+ * Host buffers; H2D of y and D2H of u happen inside (page-locked buffers that are mapped into the
+ * device -- u 16-byte aligned -- are read and written by the kernels themselves, with no copy on the stream).
  * CMPC_ERR_STATE after a closed-loop run on the same handle (cmpc_run_closed_loop*): that loop
  * has already consumed the next measurement (its plant kernel runs the observer update and the
  * linearisation of the following record), so the handle needs cmpc_initialize first. */

@@ -869,6 +869,29 @@ def test_streaming_closed_loop_with_page_locked_buffers(setups, pkg, gpu_lib, ca
         assert np.array_equal(rec_al.numpy()[:, :1 + n], ref[:, 0, :1 + n])
 
 
+@pytest.mark.parametrize("case,B", [("coop-par", 45), ("cent-ser", 33)])
+def test_get_next_input_with_page_locked_buffers(setups, pkg, gpu_lib, case, B):
+    """cmpc_get_next_input with page-locked (mapped) measurement and input buffers -- the linearisation kernel
+    reads the measurements itself, the solve kernel writes the inputs straight out -- gives what the copy path
+    gives, bit for bit (ragged last block of the linearisation kernel; one and two sub-controllers)."""
+    import torch
+    s = setups[case]
+    x_def, u_def = ol.plant_defaults(s.plant)
+    rng = np.random.default_rng(5)
+    y0 = ol.plant_output(s.plant, x_def)
+    a, b = pkg.from_setup(s, batch=B), pkg.from_setup(s, batch=B)
+    for nc in (a, b):
+        nc.Initialize(x_def, np.zeros(4), u_def, y0)
+    y_pin = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+    u_pin = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+    for k in range(12):
+        y = y0 * (1 + 1e-3 * rng.uniform(-1, 1, (B, 4)))
+        u_copy = a.GetNextInput(y)
+        y_pin.copy_(torch.from_numpy(y)); u_pin.fill_(float("nan"))
+        b.GetNextInputRaw(y_pin.data_ptr(), u_pin.data_ptr())
+        assert np.array_equal(u_pin.numpy(), u_copy), k
+
+
 def test_argument_validation_added_in_round_two(setups, pkg, gpu_lib):
     import torch
     s = setups["coop-par"]
