@@ -45,7 +45,7 @@ AssembleFn assemble_variant(int p) {
 template <class S>
 int shape_setup(cmpc_handle* h) {
   const SmemLayout<S> lay(h->P.p, h->P.b_max, h->P.n_pow, stage_tiles_for(h->P.p));
-  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL) * lay.total + 8);
+  h->smem_bytes = sizeof(double) * (size_t(S::NCTRL / assemble_ctas_per_scenario<S>(h->P.p)) * lay.total + 8);
 #ifdef CMPC_PHASE_TIMING
   if (const char* e = getenv("CMPC_DEBUG_SMEM_MIN")) { size_t m = size_t(atol(e)); if (h->smem_bytes < m) h->smem_bytes = m; }  // occupancy experiments
 #endif
@@ -59,7 +59,7 @@ int shape_setup(cmpc_handle* h) {
   CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (getenv("CMPC_DEBUG")) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, S::NCTRL * S::TPC, h->smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, assemble_block_threads<S>(h->P.p), h->smem_bytes);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, fn);
     fprintf(stderr, "[cmpc] assemble_kernel: smem %zu B/CTA, %d regs, %zu B local, occupancy %d CTAs/SM\n",
@@ -103,7 +103,7 @@ int launch_step_impl(cmpc_handle* h, const double* y, double* u, cudaStream_t st
   }
   if (ev) CU(cudaEventRecord(ev[1], st));
   // K1: discretisation, prediction, QP assembly; one CTA per scenario
-  CU(launch_pdl(assemble_variant<S>(h->cfg.p), B, S::NCTRL * S::TPC, h->smem_bytes, st, h->P, h->G, y));
+  CU(launch_pdl(assemble_variant<S>(h->cfg.p), B * assemble_ctas_per_scenario<S>(h->P.p), assemble_block_threads<S>(h->P.p), h->smem_bytes, st, h->P, h->G, y));
   if (ev) CU(cudaEventRecord(ev[2], st));
   // K2: Jacobi sweeps + update; one lane pair per scenario
   const unsigned solve_grid = (B * S::NCTRL + 63) / 64;

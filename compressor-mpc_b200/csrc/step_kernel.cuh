@@ -76,6 +76,24 @@ __host__ __device__ constexpr int stage_tiles_for(int p) { return p == 200 ? 36 
 __host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : 4; }
 #endif
 
+// assemble_kernel runs one CTA per scenario with a 64-thread group per sub-controller, or one 64-thread CTA
+// per (scenario, sub-controller): the groups never meet inside the kernel.  A 64-thread CTA hands back its
+// registers and shared memory as soon as ITS sub-controller is done, which is worth 2 % at p = 100
+// (103.2 -> 101.2 us per launch of 4096 scenarios); at p = 200 the 128-thread form is 1.3 % ahead
+// (2450 vs 2484 us), so the split is tied to the horizon.  -DCMPC_NO_SPLIT_CTA builds the 128-thread form
+// everywhere (A/B builds).
+template <class S>
+__host__ __device__ constexpr int assemble_ctas_per_scenario(int pct) {
+#ifdef CMPC_NO_SPLIT_CTA
+  (void)pct;
+  return 1;
+#else
+  return pct == 100 ? S::NCTRL : 1;
+#endif
+}
+template <class S>
+__host__ __device__ constexpr int assemble_block_threads(int pct) { return S::NCTRL * S::TPC / assemble_ctas_per_scenario<S>(pct); }
+
 // offsets inside one controller's global state record
 constexpr int kOffXhat = 0, kOffDx = 16, kOffYold = 112, kOffUold = 116;
 
@@ -140,9 +158,14 @@ struct DeviceState {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Barrier of one controller group.  The id sits in a register, so ptxas reserves all 16 named barriers for
+// the CTA ("used 16 barriers"), and an SM has 64: at most FOUR such CTAs per SM, whatever their size.  The
+// 128-thread form of assemble_kernel is at 3 or 4 CTAs per SM anyway; the 64-thread form (eight per SM) must
+// use a barrier with an immediate id (cta_sync).
 __device__ __forceinline__ void group_sync(int g, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 // Columns of the giant-step matrix R.  Table rows k >= p - 40 are never read through a delayed
 // input column (those read 40 rows back) and rows k >= p - 39 never through the X40 column, so the
@@ -555,7 +578,7 @@ lin_kernel(StepParams P, DeviceState G, double* __restrict__ y, const double* __
 }
 
 #ifdef CMPC_PHASE_TIMING
-#define CMPC_TICK(i) do { if (threadIdx.x == 0) { G.ticks[size_t(blockIdx.x) * 32 + (i)] = clock64() - tick_t0_; } } while (0)
+#define CMPC_TICK(i) do { if (threadIdx.x == 0 && g == 0) { G.ticks[size_t(scen) * 32 + (i)] = clock64() - tick_t0_; } } while (0)
 #else
 #define CMPC_TICK(i) do { } while (0)
 #endif
@@ -574,24 +597,27 @@ __device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov
 // every tile count, stride and loop bound below then folds to a constant.  PCT = 0 reads them
 // from the parameters.
 template <class S, int RPT, int PCT>
-__global__ void __launch_bounds__(S::NCTRL * S::TPC, assemble_min_blocks(PCT))
+__global__ void __launch_bounds__(assemble_block_threads<S>(PCT), assemble_min_blocks(PCT) * assemble_ctas_per_scenario<S>(PCT))
 assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int kCtasPerScen = assemble_ctas_per_scenario<S>(PCT);
 #ifdef CMPC_PHASE_TIMING
-  if (threadIdx.x == 0 && blockIdx.x < P.batch) CMPC_GTIME_AT(blockIdx.x, 16);
+  if (threadIdx.x == 0 && blockIdx.x % kCtasPerScen == 0 && blockIdx.x / kCtasPerScen < P.batch) CMPC_GTIME_AT(blockIdx.x / kCtasPerScen, 16);
 #endif
   pdl_wait();
 #ifdef CMPC_PHASE_TIMING
-  if (threadIdx.x == 0 && blockIdx.x < P.batch) CMPC_GTIME_AT(blockIdx.x, 17);
+  if (threadIdx.x == 0 && blockIdx.x % kCtasPerScen == 0 && blockIdx.x / kCtasPerScen < P.batch) CMPC_GTIME_AT(blockIdx.x / kCtasPerScen, 17);
 #endif
   constexpr int N = S::N, NY = S::NY, NU = S::NU, NV = S::NV, NVO = S::NVO, NO = S::NO;
   constexpr int TPC = S::TPC, WPC = S::WPC, NOBS = S::NOBS, NSC = S::NSC, NH = S::NH;
 #ifdef CMPC_PHASE_TIMING
   const long long tick_t0_ = clock64();
 #endif
-  const int scen = blockIdx.x;
+  const int scen = blockIdx.x / kCtasPerScen;
   if (scen >= P.batch) return;
-  const int g = threadIdx.x / TPC, t = threadIdx.x % TPC;
+  // one CTA per scenario with a thread group per sub-controller, or (kCtasPerScen = NCTRL) one CTA per
+  // (scenario, sub-controller): the groups never meet, so either works
+  const int g = kCtasPerScen > 1 ? int(blockIdx.x % kCtasPerScen) : int(threadIdx.x / TPC), t = threadIdx.x % TPC;
   const int lane = t & 31, warp = t >> 5;
 #ifdef CMPC_POISON_SMEM
   // test builds: start from NaN-filled shared memory, so that any read of a word this launch did
@@ -613,7 +639,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   constexpr int kStageTiles = stage_tiles_for(PCT);
   const SmemLayout<S> lay(p, b_max, n_pow, kStageTiles);
   const int ldE = lay.ldE;
-  double* sm = smem + g * lay.total;
+  double* sm = smem + (kCtasPerScen > 1 ? 0 : g * lay.total);
+  auto gsync = [&]() {
+    if constexpr (kCtasPerScen > 1) cta_sync();
+    else group_sync(g, TPC);
+  };
   const double* gs = G.ctrl + (size_t(scen) * S::NCTRL + g) * kCtrlStateStride;
   double* wk = G.work + (size_t(scen) * S::NCTRL + g) * kWorkStride;
 
@@ -641,7 +671,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  group_sync(g, TPC);
+  gsync();
   if (t == 0) {
     constexpr unsigned kBytesA = kNNP * 8, kBytesC = 4 * N * 8;
     static_assert(kBytesA % 16 == 0 && kBytesC % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -709,7 +739,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     if (t + k * TPC < 2 * kDelay) q[t + k * TPC] = q_v[k];
   if (t < 4) yv[t] = yd_v;
   else if (t < 8) dxd[t - 4] = yd_v;
-  group_sync(g, TPC);
+  gsync();
 
   CMPC_TICK(0);
   // ---- phase 3: DiscretizeRK4 (aug_lin_sys.cc:232-255) on the FP64 tensor cores -------------
@@ -725,25 +755,25 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     mma3_shared_a<3>(cc, a, bb, 2);
     tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
     tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
-    group_sync(g, TPC);
+    gsync();
     frag_a(A2, kLD, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 2);
     tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
     tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
-    group_sync(g, TPC);
+    gsync();
     const double k1 = P.rk[0], k2 = P.rk[1], k3 = P.rk[2], k4 = P.rk[3];
     for (int idx = t; idx < kNNP; idx += TPC) {   // pads included: they come out as exact zeros
       const int i = idx / kLD, j = idx % kLD;
       Acom[idx] = k1 * ((i == j && i < N) ? 1.0 : 0.0) + k2 * Ac[idx] + k3 * A2[idx] + k4 * A3[idx];
     }
-    group_sync(g, TPC);
+    gsync();
     // Ad = I + Acom Ac (into the A2 slot), [Bd | fd] = Acom Xc
     frag_a(Acom, kLD, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 3);
     tile_store<true>(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0], N);
     tile_store<true>(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1], N);
     tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
-    group_sync(g, TPC);
+    gsync();
   }
   double* Pw = scr + kNNP;  // Ad lives in the A2 slot: Pw[j] = Ad^(2^j) = scr + (1 + j) kNNP
   if (G.lin) {
@@ -770,7 +800,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   }
   for (int idx = t; idx < kLD * 2; idx += TPC)
     V[(idx >> 1) * kLDV + (idx & 1)] = ((idx >> 1) < N) ? BF[(idx >> 1) * kNC + 1 + 2 * (idx & 1)] : 0.0;
-  group_sync(g, TPC);
+  gsync();
   // The stages are unrolled with a compile-time index: every stage but the last one of the run has
   // compile-time tile counts, so its DMMAs are straight-line code with nothing to predicate.
   auto stage = [&](auto Jc) {
@@ -801,7 +831,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
           if (b + 1 < 5) U[(b + 1) * kLD + i] = cu[1];
         }
       }
-      group_sync(g, TPC);
+      gsync();
       if (warp == 0) {
         // Z_b = state at the start of delay block b (Z_0 = 0) goes to V[:, b]: phase 5 turns it
         // into C~ Ad^a Z_b for the rows that still see a partially drained delay line
@@ -829,7 +859,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         }
         if (lane < N) R[lane * ldr + 5] = z;
       }
-      group_sync(g, TPC);
+      gsync();
       CMPC_TICK(8);
     }
     if (s > n_pow) return;   // horizons of at most 8 rows have no giant step: the ladder ends after the baby stages
@@ -954,7 +984,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         }
       }
     }
-    group_sync(g, TPC);
+    gsync();
   };
   stage(std::integral_constant<int, 0>{});
   stage(std::integral_constant<int, 1>{});
@@ -1020,7 +1050,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
           mma3_shared_b<NY>(acc[i], al, b);
         }
       }
-      group_sync(g, TPC);   // L, R and the powers are dead: E overwrites them
+      gsync();   // L, R and the powers are dead: E overwrites them
 #pragma unroll
       for (int i = 0; i < MAXNT; ++i) {
         const int nt = warp + i * WPC;
@@ -1039,7 +1069,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       }
     }
   }
-  group_sync(g, TPC);
+  gsync();
   if (G.etab) {
     double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NY * 5);
     for (int idx = t; idx < p * NY * 5; idx += TPC) {
@@ -1103,7 +1133,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       off[c] = v - tot[c];                       // exclusive prefix inside the warp
       if (lane == 31) carry[warp * NSC + c] = v;  // warp total
     }
-    group_sync(g, TPC);
+    gsync();
 #pragma unroll
     for (int c = 0; c < NSC; ++c)
       for (int w = 0; w < warp; ++w) off[c] += carry[w * NSC + c];
@@ -1223,11 +1253,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       for (int i = 0; i < 16; ++i) hi[i] = (32 + i < S::NACC) ? acc[32 + i] : 0.0;
       tot_hi = warp_transpose_reduce<16>(hi, lane);
     }
-    group_sync(g, TPC);  // E is dead: reuse it as the exchange buffer
+    gsync();  // E is dead: reuse it as the exchange buffer
     double* red = E;
     red[warp * RS + lane] = tot_lo;
     if (S::NACC > 32 && lane < 16) red[warp * RS + 32 + lane] = tot_hi;
-    group_sync(g, TPC);
+    gsync();
     if (t < S::NACC) {
       double v = red[t];
 #pragma unroll
@@ -1259,7 +1289,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     wk[kWBF + 2 * N + t] = BF[t * kNC + 2];
   }
 #ifdef CMPC_PHASE_TIMING
-  if (threadIdx.x == 0) CMPC_GTIME_AT(blockIdx.x, 18);
+  if (threadIdx.x == 0 && g == 0) CMPC_GTIME_AT(scen, 18);
 #endif
 }
 

@@ -5,7 +5,7 @@
 mkdir -p gpurun_out/ab
 for v in "$@"; do
   if [ "$v" = main ]; then lib=compressor-mpc_b200/libcmpc_b200.so; else lib=build/lib_$v.so; fi
-  for rep in 1 2; do
+  for rep in $(seq 1 ${REPS:-2}); do
     CMPC_B200_LIB=$PWD/$lib python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-b1 --sweep-steps 40 \
         > gpurun_out/ab/$v.$rep.json 2> gpurun_out/ab/$v.$rep.err || tail -3 gpurun_out/ab/$v.$rep.err
     python - "$v" "$rep" <<'PY'
