@@ -73,7 +73,10 @@ __host__ __device__ constexpr int stage_tiles_for(int) { return kMaxStageTiles; 
 __host__ __device__ constexpr int assemble_min_blocks(int) { return 4; }
 #else
 __host__ __device__ constexpr int stage_tiles_for(int p) { return p == 200 ? 36 : kMaxStageTiles; }
-__host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : 4; }
+#ifndef CMPC_ASM_MINB100
+#define CMPC_ASM_MINB100 4
+#endif
+__host__ __device__ constexpr int assemble_min_blocks(int pct) { return pct == 200 ? 3 : pct == 100 ? CMPC_ASM_MINB100 : 4; }
 #endif
 
 // assemble_kernel runs one CTA per scenario with a 64-thread group per sub-controller, or one 64-thread CTA
@@ -214,7 +217,8 @@ struct SmemLayout {
     cz = take(kDelay * S::NY);
     mbar = take(2);   // transaction barrier of the bulk-copy staging
     region = o;
-    const int n_scr = (n_pow + 1 > 6 ? n_pow + 1 : 6) * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then Ad^(2^j)
+    (void)n_pow;
+    const int n_scr = 5 * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then the powers Ad^(2^j) alternate between the A2 and A3 slots
     // E is channel-major: E[(y kNC + c) ldE + r].  ldE = 2 mod 4 keeps the 16-byte row-pair loads of
     // phase 6 aligned and spreads the four column pairs of a DMMA output tile over all banks.
     ldE = kBaby * b_max + 2;
@@ -775,7 +779,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
     gsync();
   }
-  double* Pw = scr + kNNP;  // Ad lives in the A2 slot: Pw[j] = Ad^(2^j) = scr + (1 + j) kNNP
+  double* Pw = scr + kNNP;  // Ad lives in the A2 slot; the powers Ad^(2^j) alternate between this slot and the next
   if (G.lin) {
     double* gl = G.lin + (size_t(scen) * S::NCTRL + g) * (N * N + N * 5);
     for (int idx = t; idx < N * N + N * 5; idx += TPC)
@@ -806,8 +810,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   auto stage = [&](auto Jc) {
     constexpr int j = decltype(Jc)::value, s = j + 1;
     if (s > n_pow + (j == 3 ? 1 : 0)) return;   // (the delay-line block of stage 3 below runs even if stage 3 does not)
-    const double* Pm = Pw + j * kNNP;
-    double* Pn = Pw + s * kNNP;
+    const double* Pm = Pw + (j & 1) * kNNP;   // a stage only reads Ad^(2^j) and writes Ad^(2^(j+1)): two slots take turns
+    double* Pn = Pw + (s & 1) * kNNP;
     if constexpr (j == 3) {
       CMPC_TICK(9);
       // X40 = P(P(P(P U_0 + U_1) + U_2) + U_3) + U_4 with U_b = sum_{a,d} V_(7-a)[:, d] q_d[8b + a],
