@@ -202,7 +202,7 @@ __host__ __device__ constexpr int ladder_stages(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int yv, dxd, q, Cc, BF, carry, U, cz, mbar, region, L, R, V, lr_end, E, ldE, total;
+  int yv, dxd, q, Cc, BF, carry, U, cz, mbar, bp, ldBP, e0, lt, region, L, R, V, lr_end, E, ldE, total;
   bool e_alias;
   __host__ __device__ SmemLayout(int p, int b_max, int n_pow, int max_stage_tiles) {
     int o = 0;
@@ -216,6 +216,9 @@ struct SmemLayout {
     U = take(6 * kLD);
     cz = take(kDelay * S::NY);
     mbar = take(2);   // transaction barrier of the bulk-copy staging
+    ldBP = b_max;
+    bp = take(S::NSC * ldBP);          // block prefixes of the scan channels (prefix-table form of phase 6)
+    e0 = take(S::NY * 2 * kBaby);      // the delayed-input columns of the first table block, undifferenced
     region = o;
     (void)n_pow;
     const int n_scr = 5 * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then the powers Ad^(2^j) alternate between the A2 and A3 slots
@@ -235,6 +238,13 @@ struct SmemLayout {
     const int r_cols = giant_cols(b_max, full_blocks(p, b_max));
     V = R + kLD * giant_stride(r_cols);     // 12 rows: rows >= N stay zero (K padding)
     lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
+    // cumulative baby steps (prefix-table form): over the dead RK4 scratch when E is written after a barrier
+    // (e_alias), else behind V
+    lt = region;
+    if (!e_alias) {
+      lt = lr_end;
+      lr_end += kBaby * S::NY * kLD;
+    }
     int end = lr_end > region + e_size ? lr_end : region + e_size;
     if (end < E + red_size) end = E + red_size;
     total = (end + 1) & ~1;
@@ -655,6 +665,13 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   double* BF = sm + lay.BF; double* scr = sm + lay.region; double* U = sm + lay.U;
   double* L = sm + lay.L; double* R = sm + lay.R; double* V = sm + lay.V; double* E = sm + lay.E;
   double* carry = sm + lay.carry; double* CZ = sm + lay.cz;
+  double* BP = sm + lay.bp; double* E0 = sm + lay.e0; double* LT = sm + lay.lt;
+  const int ldBP = lay.ldBP;
+#ifdef CMPC_SCAN_BY_SHUFFLE   // (A/B builds) prefix sums over the horizon by a register / shuffle scan
+  constexpr bool kPT = false;
+#else
+  constexpr bool kPT = true;
+#endif
   double* Ac = scr;                 // continuous A (stride kLD)
   double* A2 = scr + kNNP;
   double* A3 = scr + 2 * kNNP;
@@ -1003,11 +1020,28 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   CMPC_TICK(2);
   // ---- phase 5: E[a + 8b][y][c] = (L_a R_b)[y][c]: (8 NY x N) (N x b_max kNC) on the tensor cores ----
   // warp w takes the column blocks nt = w, w + WPC, ...; the NY row blocks of L stay in registers.
+  // Prefix-table form (kPT): the left factor is the running sum of the baby steps, LT_a = sum_{a' <= a} L_a', so
+  // the table holds T[8 b + a] = sum_{k = 8 b}^{8 b + a} E_k, the prefix sum of the impulse response INSIDE its block
+  // of 8 rows.  E_r is then a difference of two neighbouring entries, and the prefix sums over the whole horizon
+  // that Su and Sf need are T plus the block prefix BP[b] = sum_{b' < b} T[8 b' + 7] (13 serial additions per
+  // channel), instead of a 15-channel shuffle scan over the 64 threads of the group (150 shuffles per warp).
+  if constexpr (kPT) {
+    for (int idx = t; idx < NY * kLD; idx += TPC) {
+      const int yy = idx / kLD, j = idx % kLD;
+      double sacc = 0.0;
+#pragma unroll
+      for (int a = 0; a < kBaby; ++a) {
+        sacc += L[(yy * kBaby + a) * kLD + j];
+        LT[(yy * kBaby + a) * kLD + j] = sacc;
+      }
+    }
+    gsync();
+  }
   {
     const int n_nt = (r_cols_all + 7) >> 3;
     double al[NY][3];
 #pragma unroll
-    for (int mt = 0; mt < NY; ++mt) frag_a(L, kLD, mt, lane, al[mt]);
+    for (int mt = 0; mt < NY; ++mt) frag_a(kPT ? LT : L, kLD, mt, lane, al[mt]);
     // row block mt of L is output mt, its rows are the baby steps a: a lane's two results are
     // channels (cc, cc + 1) of row a + 8 b (cc is even, so both stay inside block b)
     auto store_e = [&](int mt, int nt, const double (&c)[2]) {
@@ -1030,7 +1064,14 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       // CZ[r][y] = (L_a Z_b)[y] with r + 1 = 8 b + a: the block-state part of Sx x_aug for r < 39
       double bz[3], czz[NY][2];
       frag_b(V, kLDV, 0, lane, bz);
-      mma3_shared_b<NY>(czz, al, bz);
+      if constexpr (kPT) {
+        double alz[NY][3];   // the baby steps themselves
+#pragma unroll
+        for (int mt = 0; mt < NY; ++mt) frag_a(L, kLD, mt, lane, alz[mt]);
+        mma3_shared_b<NY>(czz, alz, bz);
+      } else {
+        mma3_shared_b<NY>(czz, al, bz);
+      }
 #pragma unroll
       for (int mt = 0; mt < NY; ++mt) {
         const double (&cz)[2] = czz[mt];
@@ -1074,12 +1115,32 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     }
   }
   gsync();
+  if constexpr (kPT) {
+    for (int idx = t; idx < NSC + NY * 2 * kBaby; idx += TPC) {
+      if (idx < NSC) {
+        const int yy = idx / kNS, c = idx % kNS;
+        const double* e = E + (yy * kNC + c) * ldE + (kBaby - 1);
+        const int nb = (c == 1 || c == 3) ? b_full : b_max;   // delayed-input columns stop at b_full
+        double sacc = 0.0;
+        for (int b = 0; b < nb; ++b) {
+          BP[idx * ldBP + b] = sacc;
+          sacc += e[kBaby * b];
+        }
+      } else {
+        const int k = idx - NSC, a = k % kBaby, yd = k / kBaby;   // yd = 2 y + (delayed input 0 or 1)
+        const double* e = E + ((yd >> 1) * kNC + 1 + 2 * (yd & 1)) * ldE + a;
+        E0[k] = e[0] - (a ? e[-1] : 0.0);
+      }
+    }
+    gsync();
+  }
   if (G.etab) {
     double* ge = G.etab + (size_t(scen) * S::NCTRL + g) * (size_t(p) * NY * 5);
     for (int idx = t; idx < p * NY * 5; idx += TPC) {
       const int r = idx / (5 * NY), cc = idx % 5;
       // delayed-input columns do not exist in the blocks b >= b_full (and nothing reads them there)
-      ge[idx] = ((cc & 1) && r >= kBaby * b_full) ? 0.0 : E[(((idx / 5) % NY) * kNC + cc) * ldE + r];
+      const double* e = E + (((idx / 5) % NY) * kNC + cc) * ldE + r;
+      ge[idx] = ((cc & 1) && r >= kBaby * b_full) ? 0.0 : (kPT && (r & 7)) ? e[0] - e[-1] : e[0];
     }
   }
 
@@ -1090,150 +1151,223 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   //   w_r = Sf fd + Sx x_aug - (y_ref - y)   (mpc_qp_solver.cc:31-37)
   //   H = Su' Q Su + R, Gx = Su' Q Su_other, f = Su' Q w accumulated per thread, then reduced.
   // RPT = rows per thread (compile time): 2 covers p <= 128, 4 covers p <= 256
-  const int r0 = t * RPT;
-  // the thread's RPT rows of every channel come in as 16-byte row pairs (r0 and kDelay are
-  // multiples of RPT, so the pairs of the delayed columns are aligned too)
-  auto load_g = [&](double (&gv)[RPT][NSC]) {
-    const bool on = r0 < p, del = r0 >= kDelay;
-#pragma unroll
-    for (int y = 0; y < NY; ++y)
-#pragma unroll
-      for (int c = 0; c < kNS; ++c) {
-        const bool delayed = (c == 1 || c == 3);
-        const bool ld = on && (!delayed || del);
-        const double* src = E + (y * kNC + c) * ldE + r0 - ((delayed && del) ? kDelay : 0);
-#pragma unroll
-        for (int j = 0; j < RPT; j += 2) {
-          double2 v = make_double2(0.0, 0.0);
-          if (ld) v = *reinterpret_cast<const double2*>(src + j);
-          gv[j][y * kNS + c] = v.x;
-          gv[j + 1][y * kNS + c] = v.y;
-        }
-      }
-  };
-  double off[NSC];
-  {
-    double tot[NSC];
-#pragma unroll
-    for (int c = 0; c < NSC; ++c) tot[c] = 0.0;
-    {
-      double gv[RPT][NSC];
-      load_g(gv);
-#pragma unroll
-      for (int j = 0; j < RPT; ++j)
-        if (r0 + j < p) {
-#pragma unroll
-          for (int c = 0; c < NSC; ++c) tot[c] += gv[j][c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < NSC; ++c) {
-      double v = tot[c];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += up;
-      }
-      off[c] = v - tot[c];                       // exclusive prefix inside the warp
-      if (lane == 31) carry[warp * NSC + c] = v;  // warp total
-    }
-    gsync();
-#pragma unroll
-    for (int c = 0; c < NSC; ++c)
-      for (int w = 0; w < warp; ++w) off[c] += carry[w * NSC + c];
-  }
-  CMPC_TICK(4);
-  // Sx x_aug, delay-line part.  Rows r >= 39 read C~ Ad^(r-39) X40 from the table.  Rows r < 39
-  // see a partially drained delay line: with r + 1 = 8 b + a the state is Ad^a Z_b plus the a
-  // inputs of the current block, i.e. CZ[r] plus a short convolution (fewer than 8 taps).
-  double conv[RPT][NY];
-#pragma unroll
-  for (int j = 0; j < RPT; ++j) {
-    const int r = r0 + j;
-#pragma unroll
-    for (int y = 0; y < NY; ++y) conv[j][y] = 0.0;
-    if (r < p) {
-      if (r >= kDelay - 1) {
-#pragma unroll
-        for (int y = 0; y < NY; ++y) conv[j][y] = E[(y * kNC + 5) * ldE + r - (kDelay - 1)];
-      } else {
-        const int bb = (r + 1) >> 3, aa = (r + 1) & 7;
-#pragma unroll
-        for (int y = 0; y < NY; ++y) conv[j][y] = CZ[r * NY + y];
-        for (int i = 0; i < aa; ++i) {
-          const double* Ek = E + (aa - 1 - i);
-          const double q0 = q[8 * bb + i], q1 = q[kDelay + 8 * bb + i];
-#pragma unroll
-          for (int y = 0; y < NY; ++y)
-            conv[j][y] = fma(Ek[(y * kNC + 1) * ldE], q0, fma(Ek[(y * kNC + 3) * ldE], q1, conv[j][y]));
-        }
-      }
-    }
-  }
-  CMPC_TICK(5);
   double acc[S::NACC];
 #pragma unroll
   for (int i = 0; i < S::NACC; ++i) acc[i] = 0.0;
+  // one prediction row's share of H = Su' Q Su, Gx = Su' Q Su_other and f = Su' Q w
+  auto gram_row = [&](const double (&su)[NY][NV], const double (&so)[NY][NVO > 0 ? NVO : 1], const double (&wv)[NY]) {
+    double qs[NY][NV];
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) {
-    const int r = r0 + j;
-    if (r < p) {
-      // one row at a time (8-byte loads): both rows of a pair would not fit the register budget
-      double gv[NSC], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], qs[NY][NV], wv[NY];
-      {
-        const bool del = r >= kDelay;
+    for (int y = 0; y < NY; ++y)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        double s = 0.0;
+#pragma unroll
+        for (int y2 = 0; y2 < NY; ++y2) s = fma(P.c[g].Q[y * NY + y2], su[y2][v], s);
+        qs[y][v] = s;
+      }
+    int hi = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+      for (int v2 = v; v2 < NV; ++v2, ++hi)
+#pragma unroll
+        for (int y = 0; y < NY; ++y) acc[hi] = fma(su[y][v], qs[y][v2], acc[hi]);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+      for (int vo = 0; vo < NVO; ++vo)
 #pragma unroll
         for (int y = 0; y < NY; ++y)
+          acc[NH + v * NVO + vo] = fma(so[y][vo], qs[y][v], acc[NH + v * NVO + vo]);
 #pragma unroll
-          for (int c = 0; c < kNS; ++c) {
-            const bool delayed = (c == 1 || c == 3);
-            gv[y * kNS + c] = (!delayed || del) ? E[(y * kNC + c) * ldE + r - (delayed ? kDelay : 0)] : 0.0;
-          }
-      }
-#pragma unroll
-      for (int y = 0; y < NY; ++y) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < NU) {
-            su[y][i] = gv[y * kNS + i];
-            su[y][NU + i] = off[y * kNS + i];
-          } else if (NVO > 0) {
-            so[y][i - NU] = gv[y * kNS + i];
-            so[y][NO + i - NU] = off[y * kNS + i];
-          }
-        }
-        const int oy = P.c[g].out_idx[y];
-        const double yref = P.yref[(size_t(g) * p + r) * NY + y];
-        wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dxd[oy] + conv[j][y] - (yref - yv[oy]);
-      }
-#pragma unroll
-      for (int c = 0; c < NSC; ++c) off[c] += gv[c];
+      for (int y = 0; y < NY; ++y) acc[NH + NV * NVO + v] = fma(wv[y], qs[y][v], acc[NH + NV * NVO + v]);
+    }
+  };
+  if constexpr (!kPT) {
+    const int r0 = t * RPT;
+    // the thread's RPT rows of every channel come in as 16-byte row pairs (r0 and kDelay are
+    // multiples of RPT, so the pairs of the delayed columns are aligned too)
+    auto load_g = [&](double (&gv)[RPT][NSC]) {
+      const bool on = r0 < p, del = r0 >= kDelay;
 #pragma unroll
       for (int y = 0; y < NY; ++y)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          double s = 0.0;
+        for (int c = 0; c < kNS; ++c) {
+          const bool delayed = (c == 1 || c == 3);
+          const bool ld = on && (!delayed || del);
+          const double* src = E + (y * kNC + c) * ldE + r0 - ((delayed && del) ? kDelay : 0);
 #pragma unroll
-          for (int y2 = 0; y2 < NY; ++y2) s = fma(P.c[g].Q[y * NY + y2], su[y2][v], s);
-          qs[y][v] = s;
+          for (int j = 0; j < RPT; j += 2) {
+            double2 v = make_double2(0.0, 0.0);
+            if (ld) v = *reinterpret_cast<const double2*>(src + j);
+            gv[j][y * kNS + c] = v.x;
+            gv[j + 1][y * kNS + c] = v.y;
+          }
         }
-      int hi = 0;
+    };
+    double off[NSC];
+    {
+      double tot[NSC];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
+      for (int c = 0; c < NSC; ++c) tot[c] = 0.0;
+      {
+        double gv[RPT][NSC];
+        load_g(gv);
 #pragma unroll
-        for (int v2 = v; v2 < NV; ++v2, ++hi)
+        for (int j = 0; j < RPT; ++j)
+          if (r0 + j < p) {
 #pragma unroll
-          for (int y = 0; y < NY; ++y) acc[hi] = fma(su[y][v], qs[y][v2], acc[hi]);
+            for (int c = 0; c < NSC; ++c) tot[c] += gv[j][c];
+          }
       }
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
+      for (int c = 0; c < NSC; ++c) {
+        double v = tot[c];
 #pragma unroll
-        for (int vo = 0; vo < NVO; ++vo)
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += up;
+        }
+        off[c] = v - tot[c];                       // exclusive prefix inside the warp
+        if (lane == 31) carry[warp * NSC + c] = v;  // warp total
+      }
+      gsync();
+#pragma unroll
+      for (int c = 0; c < NSC; ++c)
+        for (int w = 0; w < warp; ++w) off[c] += carry[w * NSC + c];
+    }
+    CMPC_TICK(4);
+    // Sx x_aug, delay-line part.  Rows r >= 39 read C~ Ad^(r-39) X40 from the table.  Rows r < 39
+    // see a partially drained delay line: with r + 1 = 8 b + a the state is Ad^a Z_b plus the a
+    // inputs of the current block, i.e. CZ[r] plus a short convolution (fewer than 8 taps).
+    double conv[RPT][NY];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int r = r0 + j;
+#pragma unroll
+      for (int y = 0; y < NY; ++y) conv[j][y] = 0.0;
+      if (r < p) {
+        if (r >= kDelay - 1) {
+#pragma unroll
+          for (int y = 0; y < NY; ++y) conv[j][y] = E[(y * kNC + 5) * ldE + r - (kDelay - 1)];
+        } else {
+          const int bb = (r + 1) >> 3, aa = (r + 1) & 7;
+#pragma unroll
+          for (int y = 0; y < NY; ++y) conv[j][y] = CZ[r * NY + y];
+          for (int i = 0; i < aa; ++i) {
+            const double* Ek = E + (aa - 1 - i);
+            const double q0 = q[8 * bb + i], q1 = q[kDelay + 8 * bb + i];
+#pragma unroll
+            for (int y = 0; y < NY; ++y)
+              conv[j][y] = fma(Ek[(y * kNC + 1) * ldE], q0, fma(Ek[(y * kNC + 3) * ldE], q1, conv[j][y]));
+          }
+        }
+      }
+    }
+    CMPC_TICK(5);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int r = r0 + j;
+      if (r < p) {
+        // one row at a time (8-byte loads): both rows of a pair would not fit the register budget
+        double gv[NSC], su[NY][NV], so[NY][NVO > 0 ? NVO : 1], wv[NY];
+        {
+          const bool del = r >= kDelay;
 #pragma unroll
           for (int y = 0; y < NY; ++y)
-            acc[NH + v * NVO + vo] = fma(so[y][vo], qs[y][v], acc[NH + v * NVO + vo]);
 #pragma unroll
-        for (int y = 0; y < NY; ++y) acc[NH + NV * NVO + v] = fma(wv[y], qs[y][v], acc[NH + NV * NVO + v]);
+            for (int c = 0; c < kNS; ++c) {
+              const bool delayed = (c == 1 || c == 3);
+              gv[y * kNS + c] = (!delayed || del) ? E[(y * kNC + c) * ldE + r - (delayed ? kDelay : 0)] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int y = 0; y < NY; ++y) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < NU) {
+              su[y][i] = gv[y * kNS + i];
+              su[y][NU + i] = off[y * kNS + i];
+            } else if (NVO > 0) {
+              so[y][i - NU] = gv[y * kNS + i];
+              so[y][NO + i - NU] = off[y * kNS + i];
+            }
+          }
+          const int oy = P.c[g].out_idx[y];
+          const double yref = P.yref[(size_t(g) * p + r) * NY + y];
+          wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dxd[oy] + conv[j][y] - (yref - yv[oy]);
+        }
+#pragma unroll
+        for (int c = 0; c < NSC; ++c) off[c] += gv[c];
+        gram_row(su, so, wv);
+      }
+    }
+  } else {
+    // Prefix-table form: thread t owns rows t, t + 64, ... (unit-stride, conflict-free 8-byte loads).  Per row and
+    // channel: T[r], T[r - 1] (inside the block) and the block prefix give E_r = T[r] - T[r - 1], the exclusive
+    // prefix BP + T[r - 1] and, for the f_d column, the inclusive one BP + T[r].
+    CMPC_TICK(4);
+    CMPC_TICK(5);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int r = t + j * TPC;
+      if (r < p) {
+        // Sx x_aug, delay-line part (see the scan form above): rows r >= 39 read C~ Ad^(r-39) X40 from the table,
+        // rows r < 39 take CZ[r] plus a short convolution with the first block of the delayed-input columns
+        double cv[NY];
+        if (r >= kDelay - 1) {
+          const int k = r - (kDelay - 1);
+#pragma unroll
+          for (int y = 0; y < NY; ++y) {
+            const double* e5 = E + (y * kNC + 5) * ldE + k;
+            cv[y] = e5[0] - ((k & 7) ? e5[-1] : 0.0);
+          }
+        } else {
+          const int bb = (r + 1) >> 3, aa = (r + 1) & 7;
+#pragma unroll
+          for (int y = 0; y < NY; ++y) cv[y] = CZ[r * NY + y];
+          for (int i = 0; i < aa; ++i) {
+            const double* e0 = E0 + (aa - 1 - i);
+            const double q0 = q[8 * bb + i], q1 = q[kDelay + 8 * bb + i];
+#pragma unroll
+            for (int y = 0; y < NY; ++y)
+              cv[y] = fma(e0[(2 * y) * kBaby], q0, fma(e0[(2 * y + 1) * kBaby], q1, cv[y]));
+          }
+        }
+        double su[NY][NV], so[NY][NVO > 0 ? NVO : 1], wv[NY];
+        const bool del = r >= kDelay;
+#pragma unroll
+        for (int y = 0; y < NY; ++y) {
+#pragma unroll
+          for (int c = 0; c < kNS; ++c) {
+            const bool delayed = (c == 1 || c == 3);
+            double gvv = 0.0, ex = 0.0, inc = 0.0;
+            if (!delayed || del) {
+              const int rr = r - (delayed ? kDelay : 0);
+              const double* e = E + (y * kNC + c) * ldE + rr;
+              const double cur = e[0], prev = (rr & 7) ? e[-1] : 0.0, bpv = BP[(y * kNS + c) * ldBP + (rr >> 3)];
+              gvv = cur - prev;
+              ex = bpv + prev;
+              inc = bpv + cur;
+            }
+            if (c < 4) {
+              if (c < NU) {
+                su[y][c] = gvv;
+                su[y][NU + c] = ex;
+              } else if (NVO > 0) {
+                so[y][c - NU] = gvv;
+                so[y][NO + c - NU] = ex;
+              }
+            } else {
+              const int oy = P.c[g].out_idx[y];
+              const double yref = P.yref[(size_t(g) * p + r) * NY + y];
+              wv[y] = inc + dxd[oy] + cv[y] - (yref - yv[oy]);
+            }
+          }
+        }
+        gram_row(su, so, wv);
       }
     }
   }
