@@ -221,7 +221,9 @@ struct SmemLayout {
     e0 = take(S::NY * 2 * kBaby);      // the delayed-input columns of the first table block, undifferenced
     region = o;
     (void)n_pow;
-    const int n_scr = 5 * kNNP;   // RK4: Ac, A2, A3, Acom, Xc; then the powers Ad^(2^j) alternate between the A2 and A3 slots
+    // RK4: Ac, A2, A3, Acom, Xc; then the powers Ad^(2^j) alternate between the A2 and A3 slots and the running
+    // sums of the baby steps (8 NY rows) take the Acom and Xc slots, plus a sixth one for four outputs
+    const int n_scr = (kBaby * S::NY * kLD > 2 * kNNP ? 6 : 5) * kNNP;
     // E is channel-major: E[(y kNC + c) ldE + r].  ldE = 2 mod 4 keeps the 16-byte row-pair loads of
     // phase 6 aligned and spreads the four column pairs of a DMMA output tile over all banks.
     ldE = kBaby * b_max + 2;
@@ -238,9 +240,9 @@ struct SmemLayout {
     const int r_cols = giant_cols(b_max, full_blocks(p, b_max));
     V = R + kLD * giant_stride(r_cols);     // 12 rows: rows >= N stay zero (K padding)
     lr_end = V + kLD * kLDV + 8;           // + slack for fragment reads past the last row
-    // cumulative baby steps (prefix-table form): over the dead RK4 scratch when E is written after a barrier
-    // (e_alias), else behind V
-    lt = region;
+    // cumulative baby steps (prefix-table form): in dead RK4 scratch when E is written after a barrier
+    // (e_alias: the table only overwrites the scratch once every warp holds its fragments), else behind V
+    lt = region + 3 * kNNP;   // from the Acom slot on: dead once the ladder runs
     if (!e_alias) {
       lt = lr_end;
       lr_end += kBaby * S::NY * kLD;
@@ -831,6 +833,21 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     double* Pn = Pw + (s & 1) * kNNP;
     if constexpr (j == 3) {
       CMPC_TICK(9);
+      if constexpr (kPT) {
+        // the baby steps are complete: their running sums LT_a = sum_{a' <= a} L_a' (left factor of the table
+        // product, phase 5) go to two RK4 slots nobody uses any more; the barriers of the ladder stages that
+        // follow order them in front of phase 5
+        for (int idx = t; idx < NY * kLD; idx += TPC) {
+          const int yy = idx / kLD, jj = idx % kLD;
+          double lv[kBaby];
+#pragma unroll
+          for (int a = 0; a < kBaby; ++a) lv[a] = L[(yy * kBaby + a) * kLD + jj];
+#pragma unroll
+          for (int a = 1; a < kBaby; ++a) lv[a] += lv[a - 1];
+#pragma unroll
+          for (int a = 0; a < kBaby; ++a) LT[(yy * kBaby + a) * kLD + jj] = lv[a];
+        }
+      }
       // X40 = P(P(P(P U_0 + U_1) + U_2) + U_3) + U_4 with U_b = sum_{a,d} V_(7-a)[:, d] q_d[8b + a],
       // P = Ad^8 = Pm.  Warp 0 of the group, lanes 0..N-1 hold one state each.
       // U (N x 5) = V (N x 16) Qm (16 x 5) on the tensor cores, Qm[2 va + d][b] = q_d[8 b + 7 - va]:
@@ -1025,18 +1042,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // of 8 rows.  E_r is then a difference of two neighbouring entries, and the prefix sums over the whole horizon
   // that Su and Sf need are T plus the block prefix BP[b] = sum_{b' < b} T[8 b' + 7] (13 serial additions per
   // channel), instead of a 15-channel shuffle scan over the 64 threads of the group (150 shuffles per warp).
-  if constexpr (kPT) {
-    for (int idx = t; idx < NY * kLD; idx += TPC) {
-      const int yy = idx / kLD, j = idx % kLD;
-      double sacc = 0.0;
-#pragma unroll
-      for (int a = 0; a < kBaby; ++a) {
-        sacc += L[(yy * kBaby + a) * kLD + j];
-        LT[(yy * kBaby + a) * kLD + j] = sacc;
-      }
-    }
-    gsync();
-  }
+  // (LT is formed inside the ladder, as soon as the baby steps are complete.)
   {
     const int n_nt = (r_cols_all + 7) >> 3;
     double al[NY][3];
@@ -1121,10 +1127,17 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         const int yy = idx / kNS, c = idx % kNS;
         const double* e = E + (yy * kNC + c) * ldE + (kBaby - 1);
         const int nb = (c == 1 || c == 3) ? b_full : b_max;   // delayed-input columns stop at b_full
+        // eight blocks at a time: the loads first (a store to BP might alias them for all the compiler knows)
         double sacc = 0.0;
-        for (int b = 0; b < nb; ++b) {
-          BP[idx * ldBP + b] = sacc;
-          sacc += e[kBaby * b];
+        for (int b0 = 0; b0 < nb; b0 += 8) {
+          double ev[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ev[i] = (b0 + i < nb) ? e[kBaby * (b0 + i)] : 0.0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (b0 + i < nb) BP[idx * ldBP + b0 + i] = sacc;
+            sacc += ev[i];
+          }
         }
       } else {
         const int k = idx - NSC, a = k % kBaby, yd = k / kBaby;   // yd = 2 y + (delayed input 0 or 1)
