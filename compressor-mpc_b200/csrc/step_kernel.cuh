@@ -769,6 +769,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // every N x N product is 2 x 2 output tiles of 8 x 8 with K = 12 (3 DMMA per tile); warp w of
   // the group owns the row block mt = w, so its A fragments are loaded once per product.
   const int mt_w = warp & 1;
+#ifdef CMPC_RK4_THREE_LEVELS   // (A/B builds) the products as the reference orders them: A^2, A^3, Acom, Acom [A | X]
+  const int mt_w = warp & 1;
   {
     double a[3], bb[3][3], cc[3][2];
     frag_a(Ac, kLD, mt_w, lane, a);
@@ -798,6 +800,69 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
     gsync();
   }
+#else
+  // The same polynomial with two dependent product levels instead of three (Paterson-Stockmeyer):
+  //   Ad = I + k1 A + A^2 (k2 I + k3 A + k4 A^2),   [Bd | fd] = k1 X + k2 A X + A^2 (k3 X + k4 A X)
+  // level 1 forms A^2 and A X, level 2 multiplies A^2 by M = k2 I + k3 A + k4 A^2 and Y = k3 X + k4 A X; the
+  // lower-order terms ride in registers from one epilogue to the next (same lane, same tile position).
+  {
+    double a[3], bb[3][3], cc[3][2];
+    const double k1 = P.rk[0], k2 = P.rk[1], k3 = P.rk[2], k4 = P.rk[3];
+    double* Mb = A3;     // M (stride kLD)
+    double* Yb = Acom;   // Y (stride kLD)
+    frag_a(Ac, kLD, mt_w, lane, a);
+    frag_b(Ac, kLD, 0, lane, bb[0]);
+    frag_b(Ac, kLD, 1, lane, bb[1]);
+    frag_b(Xc, kLD, 0, lane, bb[2]);
+    mma3_shared_a<3>(cc, a, bb, 3);
+    const int r = 8 * mt_w + frag_row(lane), c0 = 2 * (lane & 3);
+    double eA[2][2], tB[2];   // I + k1 A at this lane's positions of the two column tiles, k1 X + k2 A X
+    tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
+    tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = 8 * nt + c0;
+      double2 av = make_double2(0.0, 0.0);
+      if (r < kLD && col < kLD) av = *reinterpret_cast<const double2*>(Ac + r * kLD + col);
+      const double e0 = (r == col && r < N) ? 1.0 : 0.0, e1 = (r == col + 1 && r < N) ? 1.0 : 0.0;
+      eA[nt][0] = fma(k1, av.x, e0);
+      eA[nt][1] = fma(k1, av.y, e1);
+      double m[2];
+      m[0] = fma(k4, cc[nt][0], fma(k3, av.x, k2 * e0));
+      m[1] = fma(k4, cc[nt][1], fma(k3, av.y, k2 * e1));
+      tile_store(Mb, kLD, 0, 0, kLD, kLD, mt_w, nt, lane, m);
+    }
+    {
+      double2 xv = make_double2(0.0, 0.0);
+      if (r < kLD) xv = *reinterpret_cast<const double2*>(Xc + r * kLD + c0);
+      tB[0] = fma(k2, cc[2][0], k1 * xv.x);
+      tB[1] = fma(k2, cc[2][1], k1 * xv.y);
+      double yv2[2];
+      yv2[0] = fma(k4, cc[2][0], k3 * xv.x);
+      yv2[1] = fma(k4, cc[2][1], k3 * xv.y);
+      tile_store(Yb, kLD, 0, 0, kLD, 8, mt_w, 0, lane, yv2);
+    }
+    gsync();
+    frag_a(A2, kLD, mt_w, lane, a);
+    frag_b(Mb, kLD, 0, lane, bb[0]);
+    frag_b(Mb, kLD, 1, lane, bb[1]);
+    frag_b(Yb, kLD, 0, lane, bb[2]);
+    mma3_shared_a<3>(cc, a, bb, 3);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      cc[nt][0] += eA[nt][0];
+      cc[nt][1] += eA[nt][1];
+    }
+    cc[2][0] += tB[0];
+    cc[2][1] += tB[1];
+    // Ad goes to the A2 slot: a warp has read its own row block of A^2 before it writes it, and the other
+    // warp's row block is not touched
+    tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
+    tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
+    tile_store(BF, kNC, 0, 0, N, kNC, mt_w, 0, lane, cc[2]);
+    gsync();
+  }
+#endif
   double* Pw = scr + kNNP;  // Ad lives in the A2 slot; the powers Ad^(2^j) alternate between this slot and the next
   if (G.lin) {
     double* gl = G.lin + (size_t(scen) * S::NCTRL + g) * (N * N + N * 5);
