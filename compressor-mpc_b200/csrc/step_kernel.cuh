@@ -202,23 +202,30 @@ __host__ __device__ constexpr int ladder_stages(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int yv, dxd, q, Cc, BF, carry, U, cz, mbar, bp, ldBP, e0, lt, region, L, R, V, lr_end, E, ldE, total;
-  bool e_alias;
-  __host__ __device__ SmemLayout(int p, int b_max, int n_pow, int max_stage_tiles) {
+  int yv = 0, dxd = 0, q = 0, Cc = 0, BF = 0, carry = 0, U = 0, cz = 0, mbar = 0, bp = 0, ldBP = 0, e0 = 0, lt = 0, region = 0,
+      L = 0, R = 0, V = 0, lr_end = 0, E = 0, ldE = 0, total = 0;
+  bool e_alias = false;
+  __host__ __device__ static constexpr int take(int& o, int n) {
+    const int r = o;
+    o += (n + 1) & ~1;
+    return r;
+  }
+  // constexpr: with a compile-time horizon the kernel gets every offset as a constant (evaluated at run time
+  // by every thread, the strides' search loops were 3 % of the kernel's samples)
+  __host__ __device__ constexpr SmemLayout(int p, int b_max, int n_pow, int max_stage_tiles) {
     int o = 0;
-    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
-    yv = take(4);
-    dxd = take(4);
-    q = take(2 * kDelay);
-    Cc = take(4 * S::N);
-    BF = take(S::N * kNC);
-    carry = take(S::WPC * S::NSC);
-    U = take(6 * kLD);
-    cz = take(kDelay * S::NY);
-    mbar = take(2);   // transaction barrier of the bulk-copy staging
+    yv = take(o, 4);
+    dxd = take(o, 4);
+    q = take(o, 2 * kDelay);
+    Cc = take(o, 4 * S::N);
+    BF = take(o, S::N * kNC);
+    carry = take(o, S::WPC * S::NSC);
+    U = take(o, 6 * kLD);
+    cz = take(o, kDelay * S::NY);
+    mbar = take(o, 2);   // transaction barrier of the bulk-copy staging
     ldBP = b_max;
-    bp = take(S::NSC * ldBP);          // block prefixes of the scan channels (prefix-table form of phase 6)
-    e0 = take(S::NY * 2 * kBaby);      // the delayed-input columns of the first table block, undifferenced
+    bp = take(o, S::NSC * ldBP);          // block prefixes of the scan channels (prefix-table form of phase 6)
+    e0 = take(o, S::NY * 2 * kBaby);      // the delayed-input columns of the first table block, undifferenced
     region = o;
     (void)n_pow;
     // RK4: Ac, A2, A3, Acom, Xc; then the powers Ad^(2^j) alternate between the A2 and A3 slots and the running
@@ -653,7 +660,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int r_cols_all = giant_cols(b_max, b_full);   // columns of R
   const int ldr = CT ? giant_stride(giant_cols(kBmaxCt, kBfullCt)) : P.ldr, n_pow = CT ? ladder_stages(kBmaxCt) : P.n_pow;
   constexpr int kStageTiles = stage_tiles_for(PCT);
-  const SmemLayout<S> lay(p, b_max, n_pow, kStageTiles);
+  constexpr SmemLayout<S> lay_ct(CT ? PCT : 1, CT ? kBmaxCt : 1, CT ? ladder_stages(kBmaxCt > 0 ? kBmaxCt : 1) : 3, kStageTiles);
+  const SmemLayout<S> lay = CT ? lay_ct : SmemLayout<S>(p, b_max, n_pow, kStageTiles);
   const int ldE = lay.ldE;
   double* sm = smem + (kCtasPerScen > 1 ? 0 : g * lay.total);
   auto gsync = [&]() {
@@ -691,11 +699,10 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // and 1 % faster at p = 200 (2484 vs 2508 us); CMPC_NO_TMA_STAGING builds the register path.
   const unsigned mbar_s = unsigned(__cvta_generic_to_shared(sm + lay.mbar));
   if (t == 0) {
+    // barrier init, expected bytes and the copies by the same thread, in program order: the other threads meet
+    // the initialised barrier behind the group barrier further down, when their own loads are on their way
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  gsync();
-  if (t == 0) {
     constexpr unsigned kBytesA = kNNP * 8, kBytesC = 4 * N * 8;
     static_assert(kBytesA % 16 == 0 && kBytesC % 16 == 0, "bulk copies move multiples of 16 bytes");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(2 * kBytesA + kBytesC) : "memory");
@@ -747,6 +754,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   if (t < 4 * N) Cc[t] = cc_v;
 #else
   (void)a_v; (void)x_v; (void)cc_v;
+  gsync();
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
