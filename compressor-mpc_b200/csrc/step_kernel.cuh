@@ -300,6 +300,18 @@ __device__ __forceinline__ void frag_b(const double* B, int ldb, int nt, int lan
   b[1] = p[4 * ldb];
   b[2] = p[8 * ldb];
 }
+// The same for the N x N matrices (12 x 12 with their padding): the second row block (A) or column block (B) has
+// four rows / columns, held by lanes 0..15 (frag_row keeps bit 2 of the row).  The other half of the warp stays
+// out of the load -- one shared-memory wavefront per instruction instead of two -- and feeds zeros, which only
+// reach output rows / columns that are never stored.
+__device__ __forceinline__ void frag_a12(const double* A, int mt, int lane, double (&a)[3]) {
+  a[0] = a[1] = a[2] = 0.0;
+  if (mt == 0 || lane < 16) frag_a(A, kLD, mt, lane, a);
+}
+__device__ __forceinline__ void frag_b12(const double* B, int nt, int lane, double (&b)[3]) {
+  b[0] = b[1] = b[2] = 0.0;
+  if (nt == 0 || lane < 16) frag_b(B, kLD, nt, lane, b);
+}
 __device__ __forceinline__ void mma3(double (&c)[2], const double (&a)[3], const double (&b)[3]) {
   c[0] = 0.0;
   c[1] = 0.0;
@@ -781,15 +793,15 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   const int mt_w = warp & 1;
   {
     double a[3], bb[3][3], cc[3][2];
-    frag_a(Ac, kLD, mt_w, lane, a);
+    frag_a12(Ac, mt_w, lane, a);
     frag_b(Ac, kLD, 0, lane, bb[0]);
-    frag_b(Ac, kLD, 1, lane, bb[1]);
+    frag_b12(Ac, 1, lane, bb[1]);
     frag_b(Xc, kLD, 0, lane, bb[2]);
     mma3_shared_a<3>(cc, a, bb, 2);
     tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
     tile_store(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
     gsync();
-    frag_a(A2, kLD, mt_w, lane, a);
+    frag_a12(A2, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 2);
     tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0]);
     tile_store(A3, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1]);
@@ -801,7 +813,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     }
     gsync();
     // Ad = I + Acom Ac (into the A2 slot), [Bd | fd] = Acom Xc
-    frag_a(Acom, kLD, mt_w, lane, a);
+    frag_a12(Acom, mt_w, lane, a);
     mma3_shared_a<3>(cc, a, bb, 3);
     tile_store<true>(A2, kLD, 0, 0, kLD, kLD, mt_w, 0, lane, cc[0], N);
     tile_store<true>(A2, kLD, 0, 0, kLD, kLD, mt_w, 1, lane, cc[1], N);
@@ -818,9 +830,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     const double k1 = P.rk[0], k2 = P.rk[1], k3 = P.rk[2], k4 = P.rk[3];
     double* Mb = A3;     // M (stride kLD)
     double* Yb = Acom;   // Y (stride kLD)
-    frag_a(Ac, kLD, mt_w, lane, a);
+    frag_a12(Ac, mt_w, lane, a);
     frag_b(Ac, kLD, 0, lane, bb[0]);
-    frag_b(Ac, kLD, 1, lane, bb[1]);
+    frag_b12(Ac, 1, lane, bb[1]);
     frag_b(Xc, kLD, 0, lane, bb[2]);
     mma3_shared_a<3>(cc, a, bb, 3);
     const int r = 8 * mt_w + frag_row(lane), c0 = 2 * (lane & 3);
@@ -851,9 +863,9 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       tile_store(Yb, kLD, 0, 0, kLD, 8, mt_w, 0, lane, yv2);
     }
     gsync();
-    frag_a(A2, kLD, mt_w, lane, a);
+    frag_a12(A2, mt_w, lane, a);
     frag_b(Mb, kLD, 0, lane, bb[0]);
-    frag_b(Mb, kLD, 1, lane, bb[1]);
+    frag_b12(Mb, 1, lane, bb[1]);
     frag_b(Yb, kLD, 0, lane, bb[2]);
     mma3_shared_a<3>(cc, a, bb, 3);
 #pragma unroll
@@ -978,7 +990,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
     // its column block of Pm is multiplied by the rows of L (j < 3).  All products of a stage
     // are independent: their DMMAs are issued interleaved.
     double a[3];
-    frag_a(Pm, kLD, mt_w, lane, a);
+    frag_a12(Pm, mt_w, lane, a);
     if constexpr (j < 3) {
       constexpr int vc = 2 << j, l_cnt = 1 << j, n_lm = (l_cnt * NY + 7) >> 3;
       // tiles 0,1: squaring; 2: V.  While V has at most 4 columns (j < 2) they ride in the unused half
@@ -995,11 +1007,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         bq[1][1] = pb[4 * ldb];
         bq[1][2] = pb[8 * ldb];
       } else {
-        frag_b(Pm, kLD, 1, lane, bq[1]);
+        frag_b12(Pm, 1, lane, bq[1]);
         frag_b(V, kLDV, 0, lane, bq[2]);
       }
       double al[2][3], bl[3], cl[2][2];
-      frag_b(Pm, kLD, mt_w, lane, bl);      // column block nt = w of Pm
+      frag_b12(Pm, mt_w, lane, bl);      // column block nt = w of Pm
       // fragment row i of the doubling is (y, a) = (i >> j, i mod 2^j), i.e. row 8 y + a of L
       int l_row[2];
 #pragma unroll
@@ -1055,7 +1067,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       const int sq_tiles = do_sq ? 2 : 0, n_tiles = sq_tiles + f_tiles + p_tiles;
       auto load_tile = [&](int k, double (&bt)[3]) {
         if (k < sq_tiles) {
-          frag_b(Pm, kLD, k, lane, bt);
+          frag_b12(Pm, k, lane, bt);
         } else if (k < sq_tiles + f_tiles) {
           frag_b(R, ldr, k - sq_tiles, lane, bt);
         } else {
