@@ -944,7 +944,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         for (int kk = 0; kk < 4; ++kk) {
           const int k = 4 * kk + (lane & 3);
           const int vr = 8 * mt_w + (lane >> 2);   // rows past the matrix only feed rows that are dropped
-          const double av = V[(vr < kLD ? vr : 0) * kLDV + k];
+          const double av = (vr < kLD) ? V[vr * kLDV + k] : 0.0;
           const double bv = (n < 5) ? q[(k & 1) * kDelay + 8 * n + 7 - (k >> 1)] : 0.0;
           dmma_884(cu, av, bv);
         }
@@ -961,7 +961,11 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
         double z = (lane < N) ? U[lane] : 0.0;
         double pr[N];   // this lane's row of P, reused by every step
 #pragma unroll
-        for (int k = 0; k < N; ++k) pr[k] = Pm[(lane < N ? lane : 0) * kLD + k];
+        for (int k = 0; k < N; ++k) pr[k] = 0.0;
+        if (lane < N) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) pr[k] = Pm[lane * kLD + k];
+        }
         if (lane < kLD) V[lane * kLDV] = 0.0;
         for (int b = 1; b < 5; ++b) {
           if (lane < kLD) {
@@ -1018,10 +1022,13 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       for (int mt = 0; mt < n_lm; ++mt) {
         const int i = 8 * mt + (lane >> 2), yy = i >> j;
         l_row[mt] = (yy < NY) ? kBaby * yy + (i & (l_cnt - 1)) : -1;
-        const double* pl = L + (l_row[mt] < 0 ? 0 : l_row[mt]) * kLD + (lane & 3);
-        al[mt][0] = pl[0];
-        al[mt][1] = pl[4];
-        al[mt][2] = pl[8];
+        al[mt][0] = al[mt][1] = al[mt][2] = 0.0;
+        if (l_row[mt] >= 0) {   // lanes past the rows in use stay out of the load (fewer wavefronts)
+          const double* pl = L + l_row[mt] * kLD + (lane & 3);
+          al[mt][0] = pl[0];
+          al[mt][1] = pl[4];
+          al[mt][2] = pl[8];
+        }
       }
       mma3_shared_a_range<3, 0, n_sq_tiles>(cq, a, bq);
       mma3_shared_b_range<2, n_lm>(cl, al, bl);
