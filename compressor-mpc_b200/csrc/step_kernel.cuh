@@ -225,7 +225,6 @@ struct SmemLayout {
     mbar = take(o, 2);   // transaction barrier of the bulk-copy staging
     ldBP = b_max;
     bp = take(o, S::NSC * ldBP);          // block prefixes of the scan channels (prefix-table form of phase 6)
-    e0 = take(o, S::NY * 2 * kBaby);      // the delayed-input columns of the first table block, undifferenced
     region = o;
     (void)n_pow;
     // RK4: Ac, A2, A3, Acom, Xc; then the powers Ad^(2^j) alternate between the A2 and A3 slots and the running
@@ -687,7 +686,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   double* BF = sm + lay.BF; double* scr = sm + lay.region; double* U = sm + lay.U;
   double* L = sm + lay.L; double* R = sm + lay.R; double* V = sm + lay.V; double* E = sm + lay.E;
   double* carry = sm + lay.carry; double* CZ = sm + lay.cz;
-  double* BP = sm + lay.bp; double* E0 = sm + lay.e0; double* LT = sm + lay.lt;
+  double* BP = sm + lay.bp; double* LT = sm + lay.lt;
   const int ldBP = lay.ldBP;
 #ifdef CMPC_SCAN_BY_SHUFFLE   // (A/B builds) prefix sums over the horizon by a register / shuffle scan
   constexpr bool kPT = false;
@@ -1214,8 +1213,45 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   }
   gsync();
   if constexpr (kPT) {
-    for (int idx = t; idx < NSC + NY * 2 * kBaby; idx += TPC) {
-      if (idx < NSC) {
+    if (warp == 0) {
+      // Rows r < 39 see a partially drained delay line: with r + 1 = 8 bb + aa the a-priori free response is
+      // C~ Ad^aa Z_bb (CZ, phase 5) plus the aa inputs of the current block, a short convolution with the first rows
+      // of the delayed-input columns.  One lane per (block, output) forms the seven sums of its block from
+      // 16-byte loads -- the taps E_k = T[k] - T[k-1] of both delayed columns, the eight queue entries of the
+      // block -- and adds them to CZ (a loop over the taps inside the Gram phase costs 360 wavefronts per
+      // scenario, this 110).
+      for (int it = lane; it < 5 * NY; it += 32) {
+        const int bb = it / NY, yy = it % NY;
+        double tap[2][kBaby], qd[2][kBaby];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const double2* tp = reinterpret_cast<const double2*>(E + (yy * kNC + 1 + 2 * d) * ldE);
+          const double2* qp = reinterpret_cast<const double2*>(q + d * kDelay + kBaby * bb);
+#pragma unroll
+          for (int k = 0; k < kBaby / 2; ++k) {
+            const double2 tv = tp[k], qv = qp[k];
+            tap[d][2 * k] = tv.x;
+            tap[d][2 * k + 1] = tv.y;
+            qd[d][2 * k] = qv.x;
+            qd[d][2 * k + 1] = qv.y;
+          }
+#pragma unroll
+          for (int k = kBaby - 1; k > 0; --k) tap[d][k] -= tap[d][k - 1];
+        }
+#pragma unroll
+        for (int aa = 1; aa < kBaby; ++aa) {
+          double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < aa; ++i) {
+            v0 = fma(tap[0][aa - 1 - i], qd[0][i], v0);
+            v1 = fma(tap[1][aa - 1 - i], qd[1][i], v1);
+          }
+          const int r = kBaby * bb + aa - 1;
+          if (r < kDelay - 1) CZ[r * NY + yy] += v0 + v1;
+        }
+      }
+    } else {
+      for (int idx = t - 32; idx < NSC; idx += TPC - 32) {
         const int yy = idx / kNS, c = idx % kNS;
         const double* e = E + (yy * kNC + c) * ldE + (kBaby - 1);
         const int nb = (c == 1 || c == 3) ? b_full : b_max;   // delayed-input columns stop at b_full
@@ -1231,10 +1267,6 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
             sacc += ev[i];
           }
         }
-      } else {
-        const int k = idx - NSC, a = k % kBaby, yd = k / kBaby;   // yd = 2 y + (delayed input 0 or 1)
-        const double* e = E + ((yd >> 1) * kNC + 1 + 2 * (yd & 1)) * ldE + a;
-        E0[k] = e[0] - (a ? e[-1] : 0.0);
       }
     }
     gsync();
@@ -1420,7 +1452,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
       const int r = t + j * TPC;
       if (r < p) {
         // Sx x_aug, delay-line part (see the scan form above): rows r >= 39 read C~ Ad^(r-39) X40 from the table,
-        // rows r < 39 take CZ[r] plus a short convolution with the first block of the delayed-input columns
+        // rows r < 39 take CZ[r], which holds block state and short convolution by now
         double cv[NY];
         if (r >= kDelay - 1) {
           const int k = r - (kDelay - 1);
@@ -1430,16 +1462,8 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
             cv[y] = e5[0] - ((k & 7) ? e5[-1] : 0.0);
           }
         } else {
-          const int bb = (r + 1) >> 3, aa = (r + 1) & 7;
 #pragma unroll
           for (int y = 0; y < NY; ++y) cv[y] = CZ[r * NY + y];
-          for (int i = 0; i < aa; ++i) {
-            const double* e0 = E0 + (aa - 1 - i);
-            const double q0 = q[8 * bb + i], q1 = q[kDelay + 8 * bb + i];
-#pragma unroll
-            for (int y = 0; y < NY; ++y)
-              cv[y] = fma(e0[(2 * y) * kBaby], q0, fma(e0[(2 * y + 1) * kBaby], q1, cv[y]));
-          }
         }
         double su[NY][NV], so[NY][NVO > 0 ? NVO : 1], wv[NY];
         const bool del = r >= kDelay;
