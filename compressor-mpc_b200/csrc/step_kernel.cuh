@@ -3,7 +3,8 @@
 //   lin_kernel       observer a-posteriori + plant linearisation: scalar code, 4 threads per
 //                    (scenario, sub-controller), tens of thousands of threads in flight
 //   assemble_kernel  discretisation, prediction and QP assembly: small dense matrix algebra on the
-//                    FP64 tensor cores, one CTA per scenario, one thread group per sub-controller
+//                    FP64 tensor cores, one 64-thread group per (scenario, sub-controller) -- a CTA of
+//                    its own at p = 100, two groups per CTA otherwise
 //   solve_kernel     Jacobi sweeps of the QP solves, first move, a-priori observer update: one
 //                    lane pair per scenario (lane = sub-controller), the QP in registers
 // In the closed loop (plant_kernels.cuh) the plant kernel that follows also does lin_kernel's work
@@ -29,7 +30,9 @@
 //     Sx[r] x_aug = d + sum_t E_{r-t}[delayed] q[t]   (q = delay-line contents)
 // and E itself is built as a product L R of baby steps L_a = C~ Ad^a (a < 8) and giant
 // steps R_b = Ad^(8b) [Bd | fd], both obtained by repeated squaring/doubling, so the
-// sequential depth is ~log2(p) small matrix products instead of p.
+// sequential depth is ~log2(p) small matrix products instead of p.  The table is stored as its
+// running sum inside each block of 8 rows (left factor: the running sum of the baby steps); the
+// prefix sums over the whole horizon are that plus a per-block prefix, E_k a difference of neighbours.
 #pragma once
 #include <type_traits>
 #include <cuda_runtime.h>
@@ -202,7 +205,7 @@ __host__ __device__ constexpr int ladder_stages(int b_max) {
 // times: RK4 scratch -> powers Ad^(2^j) + L + R + V -> impulse-response table E -> reduction buffer.
 template <class S>
 struct SmemLayout {
-  int yv = 0, dxd = 0, q = 0, Cc = 0, BF = 0, carry = 0, U = 0, cz = 0, mbar = 0, bp = 0, ldBP = 0, e0 = 0, lt = 0, region = 0,
+  int yv = 0, dxd = 0, q = 0, Cc = 0, BF = 0, carry = 0, U = 0, cz = 0, mbar = 0, bp = 0, ldBP = 0, lt = 0, region = 0,
       L = 0, R = 0, V = 0, lr_end = 0, E = 0, ldE = 0, total = 0;
   bool e_alias = false;
   __host__ __device__ static constexpr int take(int& o, int n) {
