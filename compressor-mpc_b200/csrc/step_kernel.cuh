@@ -792,7 +792,6 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
   // the group owns the row block mt = w, so its A fragments are loaded once per product.
   const int mt_w = warp & 1;
 #ifdef CMPC_RK4_THREE_LEVELS   // (A/B builds) the products as the reference orders them: A^2, A^3, Acom, Acom [A | X]
-  const int mt_w = warp & 1;
   {
     double a[3], bb[3][3], cc[3][2];
     frag_a12(Ac, mt_w, lane, a);
