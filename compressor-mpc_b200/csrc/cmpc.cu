@@ -490,12 +490,12 @@ int cmpc_set_output_reference(cmpc_handle* h, const double* yref) {
     CU(cudaMemcpy(h->d_yref, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice));
     return CMPC_OK;
   }
-  // device layout [NCTRL][p][NY] with NY common to both controllers
+  // device layout [NCTRL][NY][p] with NY common to both controllers
   const int ny = h->cfg.n_controlled_outputs[0];
   std::vector<double> packed(size_t(h->NCTRL) * p * ny);
   for (int c = 0; c < h->NCTRL; ++c)
     for (int r = 0; r < p; ++r)
-      for (int i = 0; i < ny; ++i) packed[(size_t(c) * p + r) * ny + i] = sub[size_t(c) * p * 4 + size_t(r) * ny + i];
+      for (int i = 0; i < ny; ++i) packed[(size_t(c) * ny + i) * p + r] = sub[size_t(c) * p * 4 + size_t(r) * ny + i];
   CU(cudaMemcpy(h->d_yref, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice));
   return CMPC_OK;
 }

@@ -134,7 +134,7 @@ struct StepParams {
                          //    not depend on the new measurement
   double Ts;
   double rk[4];   // Ts, Ts^2/2, Ts^3/6, Ts^4/24: the RK4 polynomial of DiscretizeRK4, evaluated once on the host
-  const double* yref;   // [NCTRL][p][NY]
+  const double* yref;   // [NCTRL][NY][p]: the lanes of a warp own consecutive rows, so this is unit stride for them
   CtrlParams c[2];
 };
 
@@ -1435,7 +1435,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
             }
           }
           const int oy = P.c[g].out_idx[y];
-          const double yref = P.yref[(size_t(g) * p + r) * NY + y];
+          const double yref = P.yref[(size_t(g) * NY + y) * p + r];
           wv[y] = (off[y * kNS + 4] + gv[y * kNS + 4]) + dxd[oy] + conv[j][y] - (yref - yv[oy]);
         }
 #pragma unroll
@@ -1493,7 +1493,7 @@ assemble_kernel(StepParams P, DeviceState G, const double* __restrict__ y) {
               }
             } else {
               const int oy = P.c[g].out_idx[y];
-              const double yref = P.yref[(size_t(g) * p + r) * NY + y];
+              const double yref = P.yref[(size_t(g) * NY + y) * p + r];
               wv[y] = inc + dxd[oy] + cv[y] - (yref - yv[oy]);
             }
           }
